@@ -1,0 +1,107 @@
+/*
+ * microaligner_b200 -- C ABI of the B200 (sm_100a) non-linear registration hot path.
+ *
+ * The reference (VasylVaskivskyi/microaligner) is pure Python and has no FFI of its own: its
+ * native boundary is the list of cv2 / scikit-learn calls it makes on this path.  Each entry
+ * point below replaces one of those call sites (cited as path:line relative to the reference
+ * checkout) and is what a ctypes binding in the reference would load -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - images are row-major with an explicit row pitch in BYTES; flows are dense (h, w, 2)
+ *     float32, x-displacement first, exactly the layout cv2 / the reference use;
+ *   - `stream` is a cudaStream_t passed as void*; every call is stream-ordered, asynchronous,
+ *     allocation-free and re-entrant (scratch comes from the caller via *_workspace_bytes);
+ *   - return value 0 = ok, negative = error (ma_last_error() gives the text, thread-local);
+ *   - "tile geometry" (T, ov): tile (i, j) is the window [iT-ov, (i+1)T+ov) x [jT-ov, (j+1)T+ov)
+ *     of the image, zero outside it (shared_modules/slicer.py:23-118); results are stitched
+ *     from tile centres (shared_modules/stitcher.py:72-118).  Tiles are never materialised.
+ */
+#ifndef MICROALIGNER_B200_H
+#define MICROALIGNER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MA_OK 0
+#define MA_ERR_INVALID (-1)
+#define MA_ERR_CUDA (-2)
+#define MA_ERR_WORKSPACE (-3)
+
+/* pixel types of single-channel images */
+#define MA_U8 0
+#define MA_U16 1
+#define MA_F32 2
+
+int ma_version(void);
+const char* ma_last_error(void);
+
+/* ---- image pyramid: cv.pyrDown (optflow_reg/optflow_registrator.py:194) -------------------
+ * dst is ((h+1)/2, (w+1)/2); 5x5 binomial, BORDER_REFLECT_101, (s+128)>>8. dtype MA_U8|MA_U16. */
+int ma_pyrdown(const void* src, size_t src_pitch, int h, int w, int dtype,
+               void* dst, size_t dst_pitch, void* stream);
+
+/* ---- flow up-sampling: cv.pyrUp(flow*scale, dstsize) (optflow_registrator.py:140,150,164,169,212)
+ * src (h,w,2) -> dst (dh,dw,2), dh in {2h-1,2h}, dw in {2w-1,2w}; `scale` is the reference's
+ * pre-multiplication of the flow (1, 2 or 4). */
+int ma_pyrup_flow(const float* src, int h, int w, float* dst, int dh, int dw, float scale, void* stream);
+
+/* ---- Warper.warp (optflow_reg/warper.py:37-76): per-tile cv.remap(INTER_LINEAR, constant 0) of
+ * `img` by map = tile-local grid - flow, tile centres written to `out`. dtype MA_U8|MA_U16. */
+int ma_warp_tiles(const void* img, size_t img_pitch, int dtype, const float* flow, int h, int w,
+                  int T, int ov, void* out, size_t out_pitch, void* stream);
+
+/* ---- merge_two_flows per tile + stitch (optflow_reg/optflow_registrator.py:37-47, 217-240):
+ * per tile: max(f1)==0 -> f2; max(f2)==0 -> f1; else f1 + remap(f2, map = -f1).
+ * workspace: ma_merge_workspace_bytes(h, w, T). */
+size_t ma_merge_workspace_bytes(int h, int w, int T);
+int ma_merge_flows_tiles(const float* f1, const float* f2, int h, int w, int T, int ov,
+                         float* out, void* workspace, void* stream);
+
+/* ---- tiled Farneback: TileFlowCalc.calc_flow / farneback (optflow_reg/flow_calc.py:30-98) =
+ * cv.calcOpticalFlowFarneback(mov, ref, None, 0.5, 0, win, iters, 1, 1.7, FARNEBACK_GAUSSIAN)
+ * on every tile window in [tile_begin, tile_end) (row-major tile index), centres stitched into
+ * flow_out (h,w,2).  T<=0 selects the reference's untiled branch (flow_calc.py:61-64): one
+ * tile = the whole image, no overlap.  mov/ref share dtype and pitch.
+ * Workspace: ma_farneback_workspace_bytes(h, w, T, ov, n_batch) holds n_batch tiles in flight;
+ * the call loops over batches internally (all on `stream`). */
+size_t ma_farneback_workspace_bytes(int h, int w, int T, int ov, int n_batch);
+int ma_farneback_tiles(const void* mov, const void* ref, size_t pitch, int dtype, int h, int w,
+                       int T, int ov, int win, int iters, int tile_begin, int tile_end,
+                       float* flow_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- OptFlowRegistrator.dog (optflow_reg/optflow_registrator.py:249-274): min-max -> [0,1] f32,
+ * 41-tap separable Gaussians sigma 5 and 9 (REFLECT_101), difference, min-max -> u8.
+ * An all-zero input yields an all-zero u8 output.  No host synchronisation: both global
+ * reductions stay on the device.  workspace: ma_dog_workspace_bytes(h, w). Needs h,w >= 21. */
+size_t ma_dog_workspace_bytes(int h, int w);
+int ma_dog_u8(const void* src, size_t src_pitch, int dtype, int h, int w,
+              uint8_t* dst, size_t dst_pitch, void* workspace, void* stream);
+
+/* ---- mi_tiled (shared_modules/similarity_scoring.py:27-50): normalized mutual information
+ * (sklearn, arithmetic mean, natural log) of two u8 label images over consecutive chunks of
+ * `chunk` row-major elements of the dense n-element arrays; scores_out[c] (double, device) gets
+ * one NMI per chunk c < ceil(n/chunk).  workspace: ma_nmi_workspace_bytes(n, chunk). */
+size_t ma_nmi_workspace_bytes(size_t n, size_t chunk);
+int ma_nmi_chunks(const uint8_t* a, const uint8_t* b, size_t n, size_t chunk,
+                  double* scores_out, void* workspace, void* stream);
+
+/* ---- pipeline input prep (shared_modules/utils.py:75-95): z max-projection of n_pages images
+ * followed by cv.normalize(.., 0, 255, NORM_MINMAX, CV_8U). pages_host is a HOST array of n_pages
+ * device pointers (same pitch/dtype). workspace: ma_zmip_workspace_bytes(h, w, dtype). */
+size_t ma_zmip_workspace_bytes(int h, int w, int dtype);
+int ma_zmip_normalize_u8(const void* const* pages_host, int n_pages, size_t pitch, int dtype,
+                         int h, int w, uint8_t* dst, size_t dst_pitch, void* workspace, void* stream);
+
+/* ---- small helpers used by the host layer --------------------------------------------------*/
+/* global min/max of an image as two floats (device, out2[0]=min, out2[1]=max). */
+int ma_minmax(const void* src, size_t pitch, int dtype, int h, int w, float* out2, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

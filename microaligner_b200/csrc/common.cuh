@@ -1,0 +1,83 @@
+// Shared helpers for the sm_100a kernels of microaligner_b200.
+// Compiled with -fmad=false: the compiler never contracts a*b+c; every fused multiply-add in
+// this tree is an explicit __fmaf_rn / fma() because parity with OpenCV's CPU arithmetic
+// depends on where roundings happen.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include "../../include/microaligner_b200.h"
+
+namespace ma {
+
+void set_error(const std::string& s);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define MA_CUDA_CHECK(expr)                                   \
+    do {                                                      \
+        cudaError_t _e = (expr);                              \
+        if (_e != cudaSuccess) return ma::cuda_fail(_e, #expr); \
+    } while (0)
+
+#define MA_LAUNCH_CHECK(name)                                        \
+    do {                                                             \
+        cudaError_t _e = cudaGetLastError();                         \
+        if (_e != cudaSuccess) return ma::cuda_fail(_e, name);       \
+    } while (0)
+
+inline int invalid(const std::string& s) {
+    set_error(s);
+    return MA_ERR_INVALID;
+}
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Tile geometry shared by every tiled kernel (slicer.py / stitcher.py as index math).
+struct TileGeom {
+    int h, w;      // image size
+    int Th, Tw;    // tile core size (T x T; = h x w in the untiled branch)
+    int ov;        // overlap
+    int Sh, Sw;    // window size = core + 2*ov
+    int ny, nx;    // tile grid
+};
+
+static inline TileGeom make_geom(int h, int w, int T, int ov) {
+    TileGeom g;
+    g.h = h; g.w = w;
+    if (T <= 0) { g.Th = h; g.Tw = w; g.ov = 0; }
+    else { g.Th = T; g.Tw = T; g.ov = ov; }
+    g.Sh = g.Th + 2 * g.ov;
+    g.Sw = g.Tw + 2 * g.ov;
+    g.ny = (h + g.Th - 1) / g.Th;
+    g.nx = (w + g.Tw - 1) / g.Tw;
+    return g;
+}
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    // single reflection, valid for -n < i < 2n-1
+    i = i < 0 ? -i : i;
+    return i >= n ? 2 * (n - 1) - i : i;
+}
+
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// order-preserving float <-> uint key for atomicMin/atomicMax
+__device__ __forceinline__ unsigned f2key(float f) {
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(unsigned k) {
+    unsigned u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(u);
+}
+
+}  // namespace ma

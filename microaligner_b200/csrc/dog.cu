@@ -1,0 +1,359 @@
+// K6 / K9: difference-of-Gaussians prefilter, global min/max, z-max-projection + 8-bit normalise.
+//
+//   ma_dog_u8             OptFlowRegistrator.dog          (reference optflow_reg/optflow_registrator.py:249-274)
+//   ma_minmax             cv.minMaxIdx inside cv.normalize
+//   ma_zmip_normalize_u8  read_and_max_project_pages      (reference shared_modules/utils.py:75-95)
+//
+// dog() = cv.normalize(img, 0, 1, MINMAX, CV_32F) -> GaussianBlur 41x41 sigma 5 and sigma 9 ->
+// hs - ls -> cv.normalize(.., 0, 255, MINMAX, CV_8U).  Arithmetic reproduced (see oracle/cv_ops.py):
+//   * first normalise: scale = float(1/(max-min)), shift = -float(min*scale), f = fmaf(px, scale, shift)
+//   * row filter: s = 0; s = fmaf(x[j-20], k[j], s), j = 0..40 (REFLECT_101 at the image edge)
+//   * column filter (symmetric): s = x0*k20; s = fmaf(x[+j] + x[-j], k[20+j], s), j = 1..20
+//   * OpenCV's AVX2 separable filter leaves the last (w & 3) columns of the row pass and the last
+//     (w & 7) columns of the column pass to scalar code that rounds multiply and add separately;
+//     the same columns do so here, so the result is bit-identical to cv2 on an AVX2 host.
+//   * second normalise: a = float(255*(1/(dmax-dmin))), b = float(-dmin*scale), u8 = sat(rint(fmaf(d,a,b)))
+// Both global reductions stay on the device (ordered-key atomicMin/Max); nothing syncs with the host.
+#include <cmath>
+#include "common.cuh"
+
+namespace ma {
+
+struct DogTaps {
+    float k5[41], k9[41];
+};
+
+static void make_dog_taps(DogTaps& t) {
+    // cv.getGaussianKernel(41, sigma, CV_32F): exp(-x^2 / (2 sigma^2)) / sum in f64, stored as f32
+    for (int which = 0; which < 2; ++which) {
+        double sigma = which ? 9.0 : 5.0, k[41], sum = 0;
+        double scale2x = -0.5 / (sigma * sigma);
+        for (int i = 0; i < 41; ++i) {
+            double x = i - 20.0;
+            k[i] = std::exp(scale2x * x * x);
+            sum += k[i];
+        }
+        sum = 1. / sum;
+        for (int i = 0; i < 41; ++i) (which ? t.k9 : t.k5)[i] = (float)(k[i] * sum);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// min / max
+// ------------------------------------------------------------------------------------------------
+__global__ void init_minmax_keys(unsigned* keys, int npairs) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < npairs) {
+        keys[2 * i] = f2key(INFINITY);
+        keys[2 * i + 1] = f2key(-INFINITY);
+    }
+}
+
+// block-wide min/max, then ONE ordered-key atomic pair per block (same-address atomics serialise in L2)
+__device__ __forceinline__ void block_minmax_commit(float lo, float hi, unsigned* keys) {
+    __shared__ float s_lo[32], s_hi[32];
+    int tid = threadIdx.y * blockDim.x + threadIdx.x, nw = (blockDim.x * blockDim.y + 31) >> 5;
+    lo = warp_min(lo);
+    hi = warp_max(hi);
+    if ((tid & 31) == 0) { s_lo[tid >> 5] = lo; s_hi[tid >> 5] = hi; }
+    __syncthreads();
+    if (tid < 32) {
+        lo = tid < nw ? s_lo[tid] : INFINITY;
+        hi = tid < nw ? s_hi[tid] : -INFINITY;
+        lo = warp_min(lo);
+        hi = warp_max(hi);
+        if (tid == 0) {
+            atomicMin(&keys[0], f2key(lo));
+            atomicMax(&keys[1], f2key(hi));
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) minmax_kernel(const T* __restrict__ src, size_t pitch, int h, int w, unsigned* keys) {
+    float lo = INFINITY, hi = -INFINITY;
+    for (int y = blockIdx.y; y < h; y += gridDim.y) {
+        const T* row = (const T*)((const char*)src + (size_t)y * pitch);
+        for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < w; x += gridDim.x * blockDim.x) {
+            float v = (float)__ldg(row + x);
+            lo = fminf(lo, v);
+            hi = fmaxf(hi, v);
+        }
+    }
+    block_minmax_commit(lo, hi, keys);
+}
+
+__global__ void keys_to_float_kernel(const unsigned* keys, float* out2) {
+    out2[0] = key2f(keys[0]);
+    out2[1] = key2f(keys[1]);
+}
+
+// scale/shift of cv.normalize(.., 0, 1, NORM_MINMAX, CV_32F)
+__device__ __forceinline__ void norm01_coeffs(const unsigned* keys, float& a, float& b) {
+    double smin = key2f(keys[0]), smax = key2f(keys[1]);
+    double scale = (smax - smin > 2.220446049250313e-16) ? __ddiv_rn(1.0, __dsub_rn(smax, smin)) : 0.0;
+    a = (float)scale;
+    b = __fsub_rn(0.0f, (float)__dmul_rn(smin, (double)a));
+}
+// scale/shift of cv.normalize(.., 0, 255, NORM_MINMAX, CV_8U)
+__device__ __forceinline__ void norm255_coeffs(const unsigned* keys, float& a, float& b) {
+    double smin = key2f(keys[0]), smax = key2f(keys[1]);
+    double scale = __dmul_rn(255.0, (smax - smin > 2.220446049250313e-16) ? __ddiv_rn(1.0, __dsub_rn(smax, smin)) : 0.0);
+    double shift = __dsub_rn(0.0, __dmul_rn(smin, scale));
+    a = (float)scale;
+    b = (float)shift;
+}
+
+// ------------------------------------------------------------------------------------------------
+// row pass: 4 consecutive outputs per thread, both sigmas from one staged, normalised row segment
+// ------------------------------------------------------------------------------------------------
+constexpr int DOG_HT = 128;            // threads per row segment
+constexpr int DOG_HW = DOG_HT * 4;     // outputs per row segment
+constexpr int DOG_HROWS = 2;           // rows per block
+
+template <typename T>
+__global__ void __launch_bounds__(DOG_HT* DOG_HROWS) dog_row_kernel(const T* __restrict__ src, size_t pitch, int h, int w,
+                                                                     const unsigned* __restrict__ keys,
+                                                                     float* __restrict__ A5, float* __restrict__ A9, int wp,
+                                                                     const __grid_constant__ DogTaps taps) {
+    __shared__ __align__(16) float seg[DOG_HROWS][DOG_HW + 40];
+    int ry = threadIdx.y, y = blockIdx.y * DOG_HROWS + ry;
+    int xb = blockIdx.x * DOG_HW;
+    float a, b;
+    norm01_coeffs(keys, a, b);
+    if (y < h) {
+        const T* row = (const T*)((const char*)src + (size_t)y * pitch);
+        for (int i = threadIdx.x; i < DOG_HW + 40; i += DOG_HT) {
+            int xx = xb - 20 + i;
+            float v = 0.0f;
+            if (xx < w + 20) v = __fmaf_rn((float)__ldg(row + reflect101(xx, w)), a, b);
+            seg[ry][i] = v;
+        }
+    }
+    __syncthreads();
+    int x0 = xb + threadIdx.x * 4;
+    if (y >= h || x0 >= w) return;
+    float in[44];
+#pragma unroll
+    for (int q = 0; q < 11; ++q) {
+        float4 v = *reinterpret_cast<const float4*>(&seg[ry][threadIdx.x * 4 + q * 4]);
+        in[4 * q] = v.x; in[4 * q + 1] = v.y; in[4 * q + 2] = v.z; in[4 * q + 3] = v.w;
+    }
+    float s5[4] = {0.f, 0.f, 0.f, 0.f}, s9[4] = {0.f, 0.f, 0.f, 0.f};
+    if (x0 < (w & ~3)) {  // vector body of OpenCV's row filter: fused
+#pragma unroll
+        for (int j = 0; j < 41; ++j)
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                s5[o] = __fmaf_rn(in[o + j], taps.k5[j], s5[o]);
+                s9[o] = __fmaf_rn(in[o + j], taps.k9[j], s9[o]);
+            }
+    } else {  // scalar tail: multiply and add rounded separately
+#pragma unroll
+        for (int j = 0; j < 41; ++j)
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                s5[o] = __fadd_rn(s5[o], __fmul_rn(in[o + j], taps.k5[j]));
+                s9[o] = __fadd_rn(s9[o], __fmul_rn(in[o + j], taps.k9[j]));
+            }
+    }
+    size_t o = (size_t)y * wp + x0;
+    if (x0 + 3 < w) {
+        *reinterpret_cast<float4*>(A5 + o) = make_float4(s5[0], s5[1], s5[2], s5[3]);
+        *reinterpret_cast<float4*>(A9 + o) = make_float4(s9[0], s9[1], s9[2], s9[3]);
+    } else {
+        for (int q = 0; q < 4 && x0 + q < w; ++q) { A5[o + q] = s5[q]; A9[o + q] = s9[q]; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// column pass: lane <-> column, 8 consecutive rows per thread; d = blur9 - blur5; min/max of d
+// ------------------------------------------------------------------------------------------------
+constexpr int DOG_VR = 8;
+
+template <bool FUSED>
+__device__ __forceinline__ void col_conv8(const float* __restrict__ P, int wp, int h, int x, int y0, const float* k, float (&s)[DOG_VR]) {
+    float in[DOG_VR + 40];
+#pragma unroll
+    for (int q = 0; q < DOG_VR + 40; ++q) in[q] = __ldg(P + (size_t)reflect101(min(y0 - 20 + q, h + 19), h) * wp + x);
+#pragma unroll
+    for (int o = 0; o < DOG_VR; ++o) s[o] = __fmul_rn(in[o + 20], k[20]);
+#pragma unroll
+    for (int j = 1; j <= 20; ++j)
+#pragma unroll
+        for (int o = 0; o < DOG_VR; ++o) {
+            float pr = __fadd_rn(in[o + 20 + j], in[o + 20 - j]);
+            s[o] = FUSED ? __fmaf_rn(pr, k[20 + j], s[o]) : __fadd_rn(s[o], __fmul_rn(pr, k[20 + j]));
+        }
+}
+
+__global__ void __launch_bounds__(256) dog_col_kernel(const float* __restrict__ A5, const float* __restrict__ A9, int wp, int h, int w,
+                                                      float* __restrict__ D, unsigned* keys_out,
+                                                      const __grid_constant__ DogTaps taps) {
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int x = blockIdx.x * 32 + lane;
+    int y0 = (blockIdx.y * 8 + warp) * DOG_VR;
+    float lo = INFINITY, hi = -INFINITY;
+    if (x < w && y0 < h) {
+        float s5[DOG_VR], s9[DOG_VR];
+        if (x < (w & ~7)) {
+            col_conv8<true>(A5, wp, h, x, y0, taps.k5, s5);
+            col_conv8<true>(A9, wp, h, x, y0, taps.k9, s9);
+        } else {
+            col_conv8<false>(A5, wp, h, x, y0, taps.k5, s5);
+            col_conv8<false>(A9, wp, h, x, y0, taps.k9, s9);
+        }
+#pragma unroll
+        for (int o = 0; o < DOG_VR; ++o) {
+            if (y0 + o < h) {
+                float d = __fsub_rn(s9[o], s5[o]);
+                D[(size_t)(y0 + o) * wp + x] = d;
+                lo = fminf(lo, d);
+                hi = fmaxf(hi, d);
+            }
+        }
+    }
+    block_minmax_commit(lo, hi, keys_out);
+}
+
+__global__ void __launch_bounds__(256) dog_quant_kernel(const float* __restrict__ D, int wp, int h, int w,
+                                                        const unsigned* __restrict__ keys, uint8_t* __restrict__ dst, size_t dp) {
+    float a, b;
+    norm255_coeffs(keys, a, b);
+    int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+    if (x >= w) return;
+    const float* row = D + (size_t)y * wp;
+    uint8_t* out = dst + (size_t)y * dp;
+    auto q = [&](float d) { return (uint8_t)max(0, min(255, __float2int_rn(__fmaf_rn(d, a, b)))); };
+    if (x + 3 < w && ((dp & 3) == 0) && ((((uintptr_t)dst) & 3) == 0)) {
+        float4 v = *reinterpret_cast<const float4*>(row + x);
+        uchar4 u = make_uchar4(q(v.x), q(v.y), q(v.z), q(v.w));
+        *reinterpret_cast<uchar4*>(out + x) = u;
+    } else {
+        for (int i = 0; i < 4 && x + i < w; ++i) out[x + i] = q(row[x + i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// z max-projection + normalise to u8
+// ------------------------------------------------------------------------------------------------
+struct PagePtrs {
+    const void* p[64];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) zmip_kernel(PagePtrs pages, int n, size_t pitch, int h, int w, T* __restrict__ mip, int mp,
+                                                   unsigned* keys) {
+    float lo = INFINITY, hi = -INFINITY;
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x < w) {
+        for (int y = blockIdx.y; y < h; y += gridDim.y) {
+            T m = 0;
+            for (int i = 0; i < n; ++i) {
+                T v = __ldg((const T*)((const char*)pages.p[i] + (size_t)y * pitch) + x);
+                m = v > m ? v : m;
+            }
+            mip[(size_t)y * mp + x] = m;
+            lo = fminf(lo, (float)m);
+            hi = fmaxf(hi, (float)m);
+        }
+    }
+    block_minmax_commit(lo, hi, keys);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) norm_u8_kernel(const T* __restrict__ mip, int mp, int h, int w, const unsigned* __restrict__ keys,
+                                                      uint8_t* __restrict__ dst, size_t dp) {
+    float a, b;
+    norm255_coeffs(keys, a, b);
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    float v = (float)mip[(size_t)y * mp + x];
+    dst[(size_t)y * dp + x] = (uint8_t)max(0, min(255, __float2int_rn(__fmaf_rn(v, a, b))));
+}
+
+static inline int pad4(int w) { return (w + 3) / 4 * 4; }
+
+}  // namespace ma
+
+using namespace ma;
+
+extern "C" int ma_minmax(const void* src, size_t pitch, int dtype, int h, int w, float* out2, void* stream) {
+    if (!src || !out2 || h <= 0 || w <= 0) return invalid("ma_minmax: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    // out2 doubles as the key scratch (2 x 4 bytes), converted in place at the end
+    unsigned* keys = (unsigned*)out2;
+    init_minmax_keys<<<1, 32, 0, s>>>(keys, 1);
+    dim3 grid(std::min(ceil_div(w, 256), 8), std::min(h, 1184));
+    if (dtype == MA_U8) minmax_kernel<uint8_t><<<grid, 256, 0, s>>>((const uint8_t*)src, pitch, h, w, keys);
+    else if (dtype == MA_U16) minmax_kernel<uint16_t><<<grid, 256, 0, s>>>((const uint16_t*)src, pitch, h, w, keys);
+    else if (dtype == MA_F32) minmax_kernel<float><<<grid, 256, 0, s>>>((const float*)src, pitch, h, w, keys);
+    else return invalid("ma_minmax: bad dtype");
+    keys_to_float_kernel<<<1, 1, 0, s>>>(keys, out2);
+    MA_LAUNCH_CHECK("minmax_kernel");
+    return MA_OK;
+}
+
+extern "C" size_t ma_dog_workspace_bytes(int h, int w) {
+    if (h <= 0 || w <= 0) return 0;
+    return 256 + 3 * (size_t)h * pad4(w) * sizeof(float);
+}
+
+extern "C" int ma_dog_u8(const void* src, size_t src_pitch, int dtype, int h, int w,
+                         uint8_t* dst, size_t dst_pitch, void* workspace, void* stream) {
+    if (!src || !dst || !workspace) return invalid("ma_dog_u8: null pointer");
+    if (h < 21 || w < 21) return invalid("ma_dog_u8: image must be at least 21 x 21 (single-reflection border)");
+    if (dtype != MA_U8 && dtype != MA_U16) return invalid("ma_dog_u8: dtype must be MA_U8 or MA_U16");
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned* keys = (unsigned*)workspace;  // [0,1] src min/max, [2,3] diff min/max
+    int wp = pad4(w);
+    float* A5 = (float*)((char*)workspace + 256);
+    float* A9 = A5 + (size_t)h * wp;
+    float* D = A9 + (size_t)h * wp;
+    static DogTaps taps;
+    static bool taps_ready = false;
+    if (!taps_ready) { make_dog_taps(taps); taps_ready = true; }
+    init_minmax_keys<<<1, 32, 0, s>>>(keys, 2);
+    dim3 mg(std::min(ceil_div(w, 256), 8), std::min(h, 1184));
+    dim3 rg(ceil_div(w, DOG_HW), ceil_div(h, DOG_HROWS)), rb(DOG_HT, DOG_HROWS);
+    if (dtype == MA_U8) {
+        minmax_kernel<uint8_t><<<mg, 256, 0, s>>>((const uint8_t*)src, src_pitch, h, w, keys);
+        dog_row_kernel<uint8_t><<<rg, rb, 0, s>>>((const uint8_t*)src, src_pitch, h, w, keys, A5, A9, wp, taps);
+    } else {
+        minmax_kernel<uint16_t><<<mg, 256, 0, s>>>((const uint16_t*)src, src_pitch, h, w, keys);
+        dog_row_kernel<uint16_t><<<rg, rb, 0, s>>>((const uint16_t*)src, src_pitch, h, w, keys, A5, A9, wp, taps);
+    }
+    dog_col_kernel<<<dim3(ceil_div(w, 32), ceil_div(h, 8 * DOG_VR)), 256, 0, s>>>(A5, A9, wp, h, w, D, keys + 2, taps);
+    dog_quant_kernel<<<dim3(ceil_div(ceil_div(w, 4), 256), h), 256, 0, s>>>(D, wp, h, w, keys + 2, dst, dst_pitch);
+    MA_LAUNCH_CHECK("dog kernels");
+    return MA_OK;
+}
+
+extern "C" size_t ma_zmip_workspace_bytes(int h, int w, int dtype) {
+    if (h <= 0 || w <= 0) return 0;
+    return 256 + (size_t)h * pad4(w) * (dtype == MA_U8 ? 1 : 2);
+}
+
+extern "C" int ma_zmip_normalize_u8(const void* const* pages_host, int n_pages, size_t pitch, int dtype,
+                                    int h, int w, uint8_t* dst, size_t dst_pitch, void* workspace, void* stream) {
+    if (!pages_host || !dst || !workspace || h <= 0 || w <= 0) return invalid("ma_zmip_normalize_u8: bad argument");
+    if (n_pages < 1 || n_pages > 64) return invalid("ma_zmip_normalize_u8: n_pages must be in [1, 64]");
+    if (dtype != MA_U8 && dtype != MA_U16) return invalid("ma_zmip_normalize_u8: dtype must be MA_U8 or MA_U16");
+    cudaStream_t s = (cudaStream_t)stream;
+    PagePtrs pp;
+    for (int i = 0; i < n_pages; ++i) pp.p[i] = pages_host[i];
+    unsigned* keys = (unsigned*)workspace;
+    void* mip = (char*)workspace + 256;
+    int mp = pad4(w);
+    init_minmax_keys<<<1, 32, 0, s>>>(keys, 1);
+    dim3 grid(ceil_div(w, 256), h), zgrid(ceil_div(w, 256), std::min(h, 2048));
+    if (dtype == MA_U8) {
+        zmip_kernel<uint8_t><<<zgrid, 256, 0, s>>>(pp, n_pages, pitch, h, w, (uint8_t*)mip, mp, keys);
+        norm_u8_kernel<uint8_t><<<grid, 256, 0, s>>>((const uint8_t*)mip, mp, h, w, keys, dst, dst_pitch);
+    } else {
+        zmip_kernel<uint16_t><<<zgrid, 256, 0, s>>>(pp, n_pages, pitch, h, w, (uint16_t*)mip, mp, keys);
+        norm_u8_kernel<uint16_t><<<grid, 256, 0, s>>>((const uint16_t*)mip, mp, h, w, keys, dst, dst_pitch);
+    }
+    MA_LAUNCH_CHECK("zmip kernels");
+    return MA_OK;
+}

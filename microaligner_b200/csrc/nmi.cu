@@ -1,0 +1,143 @@
+// K7: normalized mutual information of two u8 label images over raster-contiguous chunks.
+//
+//   ma_nmi_chunks   mi_tiled / normalized_mutual_info_score
+//                   (reference shared_modules/similarity_scoring.py:27-50; scikit-learn
+//                    metrics/cluster/_supervised.py: arithmetic-mean normaliser, natural log)
+//
+// Per chunk: joint histogram J (256 x 256, u32, L2-resident scratch, warp-aggregated atomics),
+// then one CTA reduces it to  MI = sum_{J>0} J/n (ln J - ln n) + J/n (-ln(a_i b_j) + 2 ln n),
+// H(a), H(b) in f64 and writes NMI = MI / mean(H_a, H_b) with sklearn's special cases
+// (both labelings constant -> 1, MI == 0 -> 0).  One double per chunk leaves the kernel; the mean
+// over chunks and the `after > before` decision are taken by the host from two doubles.
+#include "common.cuh"
+
+namespace ma {
+
+constexpr int kNmiSlots = 64;                       // chunks processed per group
+constexpr size_t kHistBytes = 65536 * sizeof(unsigned);
+
+__global__ void __launch_bounds__(256) nmi_hist_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
+                                                       size_t n, size_t chunk, size_t chunk0, unsigned* __restrict__ hist) {
+    int slot = blockIdx.y;
+    size_t beg = (chunk0 + slot) * chunk;
+    size_t end = beg + chunk < n ? beg + chunk : n;
+    unsigned* H = hist + (size_t)slot * 65536;
+    size_t len = end - beg;
+    // every iteration is executed by whole warps (loop bound rounded up) so match_any sees a full mask
+    size_t iters = (len + (size_t)gridDim.x * 256 - 1) / ((size_t)gridDim.x * 256);
+    for (size_t it = 0; it < iters; ++it) {
+        size_t i = (it * gridDim.x + blockIdx.x) * 256 + threadIdx.x;
+        bool ok = i < len;
+        unsigned key = ok ? ((unsigned)__ldg(a + beg + i) << 8) | __ldg(b + beg + i) : 0xffffffffu;
+        unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (ok && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&H[key], __popc(peers));
+    }
+}
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
+    return t;
+}
+
+__global__ void __launch_bounds__(256) nmi_entropy_kernel(const unsigned* __restrict__ hist, size_t n, size_t chunk, size_t chunk0,
+                                                          double* __restrict__ scores) {
+    __shared__ unsigned pi[256], pj[256];
+    __shared__ double red[8];
+    int slot = blockIdx.x;
+    const unsigned* H = hist + (size_t)slot * 65536;
+    size_t beg = (chunk0 + slot) * chunk;
+    size_t end = beg + chunk < n ? beg + chunk : n;
+    double N = (double)(end - beg);
+    int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    pj[t] = 0;
+    __syncthreads();
+    unsigned colsum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int r = warp; r < 256; r += 8) {
+        unsigned rs = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            unsigned v = H[r * 256 + q * 32 + lane];
+            rs += v;
+            colsum[q] += v;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+        if (lane == 0) pi[r] = rs;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) atomicAdd(&pj[q * 32 + lane], colsum[q]);
+    __syncthreads();
+    double logN = log(N);
+    // entropies and class counts
+    double ha = 0, hb = 0;
+    int ca = pi[t] > 0, cb = pj[t] > 0;
+    if (ca) ha = (pi[t] / N) * (log((double)pi[t]) - logN);
+    if (cb) hb = (pj[t] / N) * (log((double)pj[t]) - logN);
+    double Ha = -block_sum(ha, red);
+    double Hb = -block_sum(hb, red);
+    int na = (int)block_sum((double)ca, red), nb = (int)block_sum((double)cb, red);
+    double mi = 0;
+    for (int r = warp; r < 256; r += 8) {
+        unsigned a_r = pi[r];
+        if (a_r == 0) continue;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            unsigned v = H[r * 256 + q * 32 + lane];
+            if (v) {
+                double cn = v / N;
+                double outer = (double)((long long)a_r * (long long)pj[q * 32 + lane]);
+                double log_outer = -log(outer) + logN + logN;
+                double term = cn * (log((double)v) - logN) + cn * log_outer;
+                if (fabs(term) < 2.220446049250313e-16) term = 0.0;
+                mi += term;
+            }
+        }
+    }
+    mi = block_sum(mi, red);
+    if (t == 0) {
+        double score;
+        if (na <= 1 && nb <= 1) score = 1.0;
+        else if (na == 1 || nb == 1) score = 0.0;
+        else {
+            if (mi < 0) mi = 0;
+            if (na == 1) Ha = 0;
+            if (nb == 1) Hb = 0;
+            score = mi == 0 ? 0.0 : mi / (0.5 * (Ha + Hb));
+        }
+        scores[chunk0 + slot] = score;
+    }
+}
+
+}  // namespace ma
+
+using namespace ma;
+
+extern "C" size_t ma_nmi_workspace_bytes(size_t n, size_t chunk) {
+    if (n == 0 || chunk == 0) return 0;
+    size_t nchunks = (n + chunk - 1) / chunk;
+    return std::min<size_t>(nchunks, kNmiSlots) * kHistBytes;
+}
+
+extern "C" int ma_nmi_chunks(const uint8_t* a, const uint8_t* b, size_t n, size_t chunk,
+                             double* scores_out, void* workspace, void* stream) {
+    if (!a || !b || !scores_out || !workspace || n == 0 || chunk == 0) return invalid("ma_nmi_chunks: bad argument");
+    if (chunk > 0xffffffffull) return invalid("ma_nmi_chunks: chunk must fit 32-bit counters");
+    cudaStream_t s = (cudaStream_t)stream;
+    size_t nchunks = (n + chunk - 1) / chunk;
+    unsigned* hist = (unsigned*)workspace;
+    for (size_t c0 = 0; c0 < nchunks; c0 += kNmiSlots) {
+        int g = (int)std::min<size_t>(kNmiSlots, nchunks - c0);
+        MA_CUDA_CHECK(cudaMemsetAsync(hist, 0, (size_t)g * kHistBytes, s));
+        int bpc = (int)std::max<size_t>(1, std::min<size_t>((chunk + 256 * 16 - 1) / (256 * 16), (size_t)(148 * 8 + g - 1) / g));
+        nmi_hist_kernel<<<dim3(bpc, g), 256, 0, s>>>(a, b, n, chunk, c0, hist);
+        nmi_entropy_kernel<<<g, 256, 0, s>>>(hist, n, chunk, c0, scores_out);
+        MA_LAUNCH_CHECK("nmi kernels");
+    }
+    return MA_OK;
+}

@@ -1,0 +1,101 @@
+// K5a / K5b: image pyramid down-sampling and flow up-sampling.
+//
+//   ma_pyrdown     cv.pyrDown(img)               (reference optflow_reg/optflow_registrator.py:194)
+//   ma_pyrup_flow  cv.pyrUp(flow*k, dstsize)     (reference optflow_reg/optflow_registrator.py:140,150,164,169,212)
+//
+// pyrDown is integer arithmetic (5x5 binomial, REFLECT_101, (s+128)>>8) -> bit-exact by construction.
+// pyrUp reproduces OpenCV's float association: rows first -- interior even (s[i-1] + 6 s[i]) + s[i+1],
+// odd (s[i]+s[i+1])*4, left edge 6 s[0] + 2 s[1], right edge s[n-2] + 7 s[n-1] and 8 s[n-1] -- then
+// the generic 3-row column form (top reflect-101, bottom replicate) times 1/64.
+#include "common.cuh"
+
+namespace ma {
+
+template <typename T>
+__global__ void __launch_bounds__(256) pyrdown_kernel(const T* __restrict__ src, size_t sp, int h, int w,
+                                                      T* __restrict__ dst, size_t dp, int oh, int ow) {
+    int ox = blockIdx.x * blockDim.x + threadIdx.x;
+    int oy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (ox >= ow || oy >= oh) return;
+    int xs[5], acc = 0;
+#pragma unroll
+    for (int d = 0; d < 5; ++d) xs[d] = reflect101(2 * ox + d - 2, w);
+    const int k[5] = {1, 4, 6, 4, 1};
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+        int yy = reflect101(2 * oy + r - 2, h);
+        const T* row = (const T*)((const char*)src + (size_t)yy * sp);
+        int s = (int)__ldg(row + xs[0]) + 4 * (int)__ldg(row + xs[1]) + 6 * (int)__ldg(row + xs[2]) +
+                4 * (int)__ldg(row + xs[3]) + (int)__ldg(row + xs[4]);
+        acc += k[r] * s;
+    }
+    *((T*)((char*)dst + (size_t)oy * dp) + ox) = (T)((acc + 128) >> 8);
+}
+
+__device__ __forceinline__ float2 mul2(float2 a, float s) { return make_float2(__fmul_rn(a.x, s), __fmul_rn(a.y, s)); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+
+// horizontally up-sampled value (unscaled, weights sum to 8) of source row `row` at output column dx
+__device__ __forceinline__ float2 up_row(const float2* __restrict__ row, int n, int dx, float scale) {
+    auto S = [&](int i) { return mul2(__ldg(row + i), scale); };
+    int i = dx >> 1;
+    if (n == 1) return mul2(S(0), 8.0f);
+    if (dx & 1) {
+        if (i == n - 1) return mul2(S(n - 1), 8.0f);
+        return mul2(add2(S(i), S(i + 1)), 4.0f);
+    }
+    if (i == 0) return add2(mul2(S(0), 6.0f), mul2(S(1), 2.0f));
+    if (i == n - 1) return add2(S(n - 2), mul2(S(n - 1), 7.0f));
+    return add2(add2(S(i - 1), mul2(S(i), 6.0f)), S(i + 1));
+}
+
+__global__ void __launch_bounds__(256) pyrup_flow_kernel(const float2* __restrict__ src, int h, int w,
+                                                         float2* __restrict__ dst, int dh, int dw, float scale) {
+    int dx = blockIdx.x * blockDim.x + threadIdx.x;
+    int dy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (dx >= dw || dy >= dh) return;
+    int i = dy >> 1;
+    int i2 = min(i + 1, h - 1);
+    float2 r1 = up_row(src + (size_t)i * w, w, dx, scale);
+    float2 r2 = up_row(src + (size_t)i2 * w, w, dx, scale);
+    float2 o;
+    if (dy & 1) {
+        o = mul2(mul2(add2(r1, r2), 4.0f), 0.015625f);
+    } else {
+        int i0 = h > 1 ? reflect101(i - 1, h) : 0;
+        float2 r0 = up_row(src + (size_t)i0 * w, w, dx, scale);
+        o = mul2(add2(add2(r0, mul2(r1, 6.0f)), r2), 0.015625f);
+    }
+    dst[(size_t)dy * dw + dx] = o;
+}
+
+}  // namespace ma
+
+using namespace ma;
+
+extern "C" int ma_pyrdown(const void* src, size_t src_pitch, int h, int w, int dtype,
+                          void* dst, size_t dst_pitch, void* stream) {
+    if (!src || !dst || h < 3 || w < 3) return invalid("ma_pyrdown: bad argument (need h,w >= 3)");
+    int oh = (h + 1) / 2, ow = (w + 1) / 2;
+    dim3 block(32, 8), grid(ceil_div(ow, 32), ceil_div(oh, 8));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == MA_U8)
+        pyrdown_kernel<uint8_t><<<grid, block, 0, s>>>((const uint8_t*)src, src_pitch, h, w, (uint8_t*)dst, dst_pitch, oh, ow);
+    else if (dtype == MA_U16)
+        pyrdown_kernel<uint16_t><<<grid, block, 0, s>>>((const uint16_t*)src, src_pitch, h, w, (uint16_t*)dst, dst_pitch, oh, ow);
+    else
+        return invalid("ma_pyrdown: dtype must be MA_U8 or MA_U16");
+    MA_LAUNCH_CHECK("pyrdown_kernel");
+    return MA_OK;
+}
+
+extern "C" int ma_pyrup_flow(const float* src, int h, int w, float* dst, int dh, int dw, float scale, void* stream) {
+    if (!src || !dst || h <= 0 || w <= 0) return invalid("ma_pyrup_flow: bad argument");
+    // cv.pyrUp accepts |dsize - 2*ssize| == dsize % 2; the reference only produces 2n and 2n-1
+    if (!((dh == 2 * h || dh == 2 * h - 1) && (dw == 2 * w || dw == 2 * w - 1)) || dh <= 0 || dw <= 0)
+        return invalid("ma_pyrup_flow: dstsize must be 2n or 2n-1 per axis");
+    dim3 block(32, 8), grid(ceil_div(dw, 32), ceil_div(dh, 8));
+    pyrup_flow_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const float2*)src, h, w, (float2*)dst, dh, dw, scale);
+    MA_LAUNCH_CHECK("pyrup_flow_kernel");
+    return MA_OK;
+}

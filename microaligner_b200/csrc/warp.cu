@@ -1,0 +1,197 @@
+// K4 / K8: bilinear remap with OpenCV's INTER_LINEAR fixed-point scheme, tiles as index math.
+//
+//   ma_warp_tiles        Warper.warp            (reference optflow_reg/warper.py:37-76)
+//   ma_merge_flows_tiles merge_two_flows+stitch (reference optflow_reg/optflow_registrator.py:37-47,217-240)
+//
+// Semantics reproduced (cv::remap, INTER_LINEAR, BORDER_CONSTANT 0, INTER_TAB_SIZE = 32):
+//   s = cvRound(map * 32) (round-half-even, "integer indefinite" on overflow), i = sat_s16(s >> 5),
+//   a = s & 31; a tap outside the S x S tile window -- or outside the image, where the window is
+//   zero padded -- contributes 0.  u8: 15-bit integer weights, (acc + 2^14) >> 15.
+//   u16 / f32: float weights (1-ay)(1-ax).. summed left to right, no FMA; u16 rounds half-even.
+//
+// HBM-bound streaming kernels: one thread per output pixel, 8-byte coalesced flow loads, the four
+// taps go through the read-only path (neighbouring threads hit the same 32-byte sectors).
+#include "common.cuh"
+
+namespace ma {
+
+__device__ __forceinline__ int cv_round_x32(float v) {
+    float p = __fmul_rn(v, 32.0f);
+    // cvtss2si: out-of-range / NaN -> 0x80000000
+    if (!(fabsf(p) < 2147483648.0f)) return (int)0x80000000;
+    return __float2int_rn(p);
+}
+__device__ __forceinline__ int sat_s16(int v) { return max(-32768, min(32767, v)); }
+
+struct Taps {
+    int ix, iy, ax, ay;
+};
+__device__ __forceinline__ Taps make_taps(float mx, float my) {
+    int sx = cv_round_x32(mx), sy = cv_round_x32(my);
+    Taps t;
+    t.ix = sat_s16(sx >> 5);
+    t.iy = sat_s16(sy >> 5);
+    t.ax = sx & 31;
+    t.ay = sy & 31;
+    return t;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) warp_tiles_kernel(const T* __restrict__ img, size_t img_pitch,
+                                                         const float2* __restrict__ flow, TileGeom g,
+                                                         T* __restrict__ out, size_t out_pitch) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= g.w || y >= g.h) return;
+    int ti = y / g.Th, tj = x / g.Tw;
+    int ty = g.ov + (y - ti * g.Th), tx = g.ov + (x - tj * g.Tw);  // tile-local pixel
+    int oy = ti * g.Th - g.ov, ox = tj * g.Tw - g.ov;              // window origin in the image
+    float2 f = __ldg(&flow[(size_t)y * g.w + x]);
+    Taps t = make_taps(__fsub_rn((float)tx, f.x), __fsub_rn((float)ty, f.y));
+
+    auto tap = [&](int yy, int xx) -> T {
+        // inside the S x S window and inside the image (window is zero padded beyond it)
+        int gy = oy + yy, gx = ox + xx;
+        bool ok = (unsigned)xx < (unsigned)g.Sw && (unsigned)yy < (unsigned)g.Sh &&
+                  (unsigned)gx < (unsigned)g.w && (unsigned)gy < (unsigned)g.h;
+        return ok ? __ldg((const T*)((const char*)img + (size_t)gy * img_pitch) + gx) : (T)0;
+    };
+    T v00 = tap(t.iy, t.ix), v01 = tap(t.iy, t.ix + 1), v10 = tap(t.iy + 1, t.ix), v11 = tap(t.iy + 1, t.ix + 1);
+    T r;
+    if (sizeof(T) == 1) {
+        int w00 = (32 - t.ay) * (32 - t.ax) * 32, w01 = (32 - t.ay) * t.ax * 32;
+        int w10 = t.ay * (32 - t.ax) * 32, w11 = t.ay * t.ax * 32;
+        int acc = (int)v00 * w00 + (int)v01 * w01 + (int)v10 * w10 + (int)v11 * w11;
+        r = (T)((acc + 16384) >> 15);
+    } else {
+        float fx = __fmul_rn((float)t.ax, 0.03125f), fy = __fmul_rn((float)t.ay, 0.03125f);
+        float ux = __fsub_rn(1.0f, fx), uy = __fsub_rn(1.0f, fy);
+        float w00 = __fmul_rn(uy, ux), w01 = __fmul_rn(uy, fx), w10 = __fmul_rn(fy, ux), w11 = __fmul_rn(fy, fx);
+        float acc = __fmul_rn((float)v00, w00);
+        acc = __fadd_rn(acc, __fmul_rn((float)v01, w01));
+        acc = __fadd_rn(acc, __fmul_rn((float)v10, w10));
+        acc = __fadd_rn(acc, __fmul_rn((float)v11, w11));
+        int q = __float2int_rn(acc);
+        r = (T)max(0, min(65535, q));
+    }
+    *((T*)((char*)out + (size_t)y * out_pitch) + x) = r;
+}
+
+// ---- merge: pass 0 = per-tile signed max of both flows over the full window (zero padding counts)
+__global__ void __launch_bounds__(256) tile_max_kernel(const float2* __restrict__ f1, const float2* __restrict__ f2,
+                                                       TileGeom g, unsigned* __restrict__ keys) {
+    // grid: (chunks, ntiles); each block scans a slice of the window rows of one tile
+    int tile = blockIdx.y;
+    int ti = tile / g.nx, tj = tile % g.nx;
+    int oy = ti * g.Th - g.ov, ox = tj * g.Tw - g.ov;
+    int y0 = max(oy, 0), y1 = min(oy + g.Sh, g.h);
+    int x0 = max(ox, 0), x1 = min(ox + g.Sw, g.w);
+    bool padded = (oy < 0) || (ox < 0) || (oy + g.Sh > g.h) || (ox + g.Sw > g.w);
+    float m1 = padded ? 0.0f : -INFINITY, m2 = m1;
+    int nw = x1 - x0, nh = y1 - y0;
+    long long total = (long long)nw * nh;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+        int yy = y0 + (int)(p / nw), xx = x0 + (int)(p % nw);
+        float2 a = __ldg(&f1[(size_t)yy * g.w + xx]);
+        float2 b = __ldg(&f2[(size_t)yy * g.w + xx]);
+        m1 = fmaxf(m1, fmaxf(a.x, a.y));
+        m2 = fmaxf(m2, fmaxf(b.x, b.y));
+    }
+    m1 = warp_max(m1);
+    m2 = warp_max(m2);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(&keys[2 * tile], f2key(m1));
+        atomicMax(&keys[2 * tile + 1], f2key(m2));
+    }
+}
+
+__global__ void init_keys_kernel(unsigned* keys, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = f2key(-INFINITY);
+}
+
+// ---- merge: pass 1 = per output pixel, branch on the tile's maxima (quirk Q3), sample f2 at the
+// ABSOLUTE tile-local coordinate -f1 (quirk Q1: the reference passes map = -flow1 to cv.remap).
+__global__ void __launch_bounds__(256) merge_tiles_kernel(const float2* __restrict__ f1, const float2* __restrict__ f2,
+                                                          TileGeom g, const unsigned* __restrict__ keys,
+                                                          float2* __restrict__ out) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= g.w || y >= g.h) return;
+    int ti = y / g.Th, tj = x / g.Tw;
+    int tile = ti * g.nx + tj;
+    size_t idx = (size_t)y * g.w + x;
+    float max1 = key2f(keys[2 * tile]), max2 = key2f(keys[2 * tile + 1]);
+    float2 a = __ldg(&f1[idx]);
+    float2 r;
+    if (max1 == 0.0f) {
+        r = __ldg(&f2[idx]);
+    } else if (max2 == 0.0f) {
+        r = a;
+    } else {
+        int oy = ti * g.Th - g.ov, ox = tj * g.Tw - g.ov;
+        Taps t = make_taps(-a.x, -a.y);
+        auto tap = [&](int yy, int xx) -> float2 {
+            int gy = oy + yy, gx = ox + xx;
+            bool ok = (unsigned)xx < (unsigned)g.Sw && (unsigned)yy < (unsigned)g.Sh &&
+                      (unsigned)gx < (unsigned)g.w && (unsigned)gy < (unsigned)g.h;
+            return ok ? __ldg(&f2[(size_t)gy * g.w + gx]) : make_float2(0.f, 0.f);
+        };
+        float2 v00 = tap(t.iy, t.ix), v01 = tap(t.iy, t.ix + 1), v10 = tap(t.iy + 1, t.ix), v11 = tap(t.iy + 1, t.ix + 1);
+        float fx = __fmul_rn((float)t.ax, 0.03125f), fy = __fmul_rn((float)t.ay, 0.03125f);
+        float ux = __fsub_rn(1.0f, fx), uy = __fsub_rn(1.0f, fy);
+        float w00 = __fmul_rn(uy, ux), w01 = __fmul_rn(uy, fx), w10 = __fmul_rn(fy, ux), w11 = __fmul_rn(fy, fx);
+        float sx = __fmul_rn(v00.x, w00), sy = __fmul_rn(v00.y, w00);
+        sx = __fadd_rn(sx, __fmul_rn(v01.x, w01)); sy = __fadd_rn(sy, __fmul_rn(v01.y, w01));
+        sx = __fadd_rn(sx, __fmul_rn(v10.x, w10)); sy = __fadd_rn(sy, __fmul_rn(v10.y, w10));
+        sx = __fadd_rn(sx, __fmul_rn(v11.x, w11)); sy = __fadd_rn(sy, __fmul_rn(v11.y, w11));
+        r.x = __fadd_rn(a.x, sx);
+        r.y = __fadd_rn(a.y, sy);
+    }
+    out[idx] = r;
+}
+
+}  // namespace ma
+
+using namespace ma;
+
+extern "C" int ma_warp_tiles(const void* img, size_t img_pitch, int dtype, const float* flow, int h, int w,
+                             int T, int ov, void* out, size_t out_pitch, void* stream) {
+    if (!img || !flow || !out || h <= 0 || w <= 0 || T <= 0 || ov < 0) return invalid("ma_warp_tiles: bad argument");
+    if (dtype != MA_U8 && dtype != MA_U16) return invalid("ma_warp_tiles: dtype must be MA_U8 or MA_U16");
+    if (T + 2 * ov > 32767) return invalid("ma_warp_tiles: tile window exceeds cv.remap's int16 coordinate range");
+    TileGeom g = make_geom(h, w, T, ov);
+    dim3 block(64, 4), grid(ceil_div(w, 64), ceil_div(h, 4));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == MA_U8)
+        warp_tiles_kernel<uint8_t><<<grid, block, 0, s>>>((const uint8_t*)img, img_pitch, (const float2*)flow, g, (uint8_t*)out, out_pitch);
+    else
+        warp_tiles_kernel<uint16_t><<<grid, block, 0, s>>>((const uint16_t*)img, img_pitch, (const float2*)flow, g, (uint16_t*)out, out_pitch);
+    MA_LAUNCH_CHECK("warp_tiles_kernel");
+    return MA_OK;
+}
+
+extern "C" size_t ma_merge_workspace_bytes(int h, int w, int T) {
+    if (h <= 0 || w <= 0 || T <= 0) return 0;
+    TileGeom g = make_geom(h, w, T, 0);
+    return (size_t)g.ny * g.nx * 2 * sizeof(unsigned);
+}
+
+extern "C" int ma_merge_flows_tiles(const float* f1, const float* f2, int h, int w, int T, int ov,
+                                    float* out, void* workspace, void* stream) {
+    if (!f1 || !f2 || !out || !workspace || h <= 0 || w <= 0 || T <= 0 || ov < 0)
+        return invalid("ma_merge_flows_tiles: bad argument");
+    if (T + 2 * ov > 32767) return invalid("ma_merge_flows_tiles: tile window exceeds int16 coordinate range");
+    TileGeom g = make_geom(h, w, T, ov);
+    cudaStream_t s = (cudaStream_t)stream;
+    int ntiles = g.ny * g.nx;
+    unsigned* keys = (unsigned*)workspace;
+    init_keys_kernel<<<ceil_div(2 * ntiles, 256), 256, 0, s>>>(keys, 2 * ntiles);
+    int chunks = max(1, min(64, (int)(((long long)g.Sh * g.Sw) / (256 * 16))));
+    if (ntiles > 65535) return invalid("ma_merge_flows_tiles: too many tiles");
+    tile_max_kernel<<<dim3(chunks, ntiles), 256, 0, s>>>((const float2*)f1, (const float2*)f2, g, keys);
+    dim3 block(64, 4), grid(ceil_div(w, 64), ceil_div(h, 4));
+    merge_tiles_kernel<<<grid, block, 0, s>>>((const float2*)f1, (const float2*)f2, g, keys, (float2*)out);
+    MA_LAUNCH_CHECK("merge_tiles_kernel");
+    return MA_OK;
+}

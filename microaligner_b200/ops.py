@@ -1,0 +1,197 @@
+"""Device operators: thin, allocation-aware wrappers of the C ABI on torch CUDA tensors.
+
+torch is used for device memory, streams and (in parallel.py) the process group only; all
+arithmetic happens in libmicroaligner_b200.so.  Images are 2-D uint8/uint16 tensors (uint16 is
+carried as torch.uint16), flows are (H, W, 2) float32 tensors, all C-contiguous on one device."""
+import ctypes
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import MA_F32, MA_U8, MA_U16, check, lib
+
+_DTYPES = {torch.uint8: MA_U8, torch.uint16: MA_U16, torch.float32: MA_F32}
+
+
+def _code(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise TypeError(f"unsupported image dtype {t.dtype}; expected uint8 or uint16") from None
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise MicroalignerDeviceError(f"{what} must live on a CUDA device (no CPU fallback)")
+    if not t.is_contiguous():
+        raise ValueError(f"{what} must be C-contiguous")
+
+
+class MicroalignerDeviceError(RuntimeError):
+    pass
+
+
+def _bytes(n: int, device) -> torch.Tensor:
+    return torch.empty(max(int(n), 16), dtype=torch.uint8, device=device)
+
+
+# --------------------------------------------------------------------------------- host <-> device
+def to_device(arr, device=None) -> torch.Tensor:
+    """numpy (uint8/uint16/float32) or torch tensor -> contiguous CUDA tensor."""
+    if isinstance(arr, torch.Tensor):
+        t = arr if arr.is_cuda else arr.to(device or "cuda")
+        return t.contiguous()
+    a = np.ascontiguousarray(arr)
+    if a.dtype not in (np.uint8, np.uint16, np.float32):
+        raise TypeError(f"unsupported dtype {a.dtype}; expected uint8, uint16 or float32")
+    return torch.from_numpy(a).to(device or "cuda", non_blocking=False)
+
+
+def to_host(t: torch.Tensor) -> np.ndarray:
+    return t.cpu().numpy()
+
+
+# --------------------------------------------------------------------------------- pyramid
+def pyr_down(img: torch.Tensor) -> torch.Tensor:
+    _req(img, "image")
+    h, w = img.shape
+    out = torch.empty(((h + 1) // 2, (w + 1) // 2), dtype=img.dtype, device=img.device)
+    es = img.element_size()
+    check(lib.ma_pyrdown(img.data_ptr(), w * es, h, w, _code(img), out.data_ptr(), out.shape[1] * es, _stream()), "ma_pyrdown")
+    return out
+
+
+def pyr_up_flow(flow: torch.Tensor, dsize_hw: Sequence[int], scale: float = 1.0) -> torch.Tensor:
+    _req(flow, "flow")
+    h, w, _ = flow.shape
+    dh, dw = int(dsize_hw[0]), int(dsize_hw[1])
+    out = torch.empty((dh, dw, 2), dtype=torch.float32, device=flow.device)
+    check(lib.ma_pyrup_flow(flow.data_ptr(), h, w, out.data_ptr(), dh, dw, float(scale), _stream()), "ma_pyrup_flow")
+    return out
+
+
+# --------------------------------------------------------------------------------- warp / merge
+def warp_tiles(img: torch.Tensor, flow: torch.Tensor, tile_size: int, overlap: int,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(img, "image")
+    _req(flow, "flow")
+    h, w = img.shape
+    if tuple(flow.shape) != (h, w, 2) or flow.dtype != torch.float32:
+        raise ValueError(f"flow must be float32 of shape {(h, w, 2)}, got {flow.dtype} {tuple(flow.shape)}")
+    if out is None:
+        out = torch.empty_like(img)
+    es = img.element_size()
+    check(lib.ma_warp_tiles(img.data_ptr(), w * es, _code(img), flow.data_ptr(), h, w, int(tile_size), int(overlap),
+                            out.data_ptr(), w * es, _stream()), "ma_warp_tiles")
+    return out
+
+
+def merge_flows_tiles(f1: torch.Tensor, f2: torch.Tensor, tile_size: int, overlap: int) -> torch.Tensor:
+    _req(f1, "flow1")
+    _req(f2, "flow2")
+    h, w, _ = f1.shape
+    out = torch.empty_like(f1)
+    ws = _bytes(lib.ma_merge_workspace_bytes(h, w, int(tile_size)), f1.device)
+    check(lib.ma_merge_flows_tiles(f1.data_ptr(), f2.data_ptr(), h, w, int(tile_size), int(overlap), out.data_ptr(),
+                                   ws.data_ptr(), _stream()), "ma_merge_flows_tiles")
+    return out
+
+
+# --------------------------------------------------------------------------------- Farneback
+_FB_WS = {}
+FARNEBACK_WORKSPACE_BUDGET = 24 << 30  # bytes of HBM the tile batch may use
+
+
+def _fb_workspace(device, nbytes: int) -> torch.Tensor:
+    ws = _FB_WS.get(device)
+    if ws is None or ws.numel() < nbytes:
+        _FB_WS.pop(device, None)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _FB_WS[device] = ws
+    return ws
+
+
+def release_workspaces():
+    _FB_WS.clear()
+
+
+def n_tiles(h: int, w: int, tile_size: int) -> int:
+    return (-(-h // tile_size)) * (-(-w // tile_size))
+
+
+def farneback_tiles(mov: torch.Tensor, ref: torch.Tensor, tile_size: int, overlap: int, win: int, iters: int,
+                    tile_range=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Stitched flow of the tiled (tile_size > 0) or untiled (tile_size <= 0) Farneback."""
+    _req(mov, "moving image")
+    _req(ref, "reference image")
+    if mov.shape != ref.shape or mov.dtype != ref.dtype:
+        raise ValueError("moving and reference image must have the same shape and dtype")
+    h, w = ref.shape
+    T = int(tile_size)
+    ntot = n_tiles(h, w, T) if T > 0 else 1
+    t0, t1 = tile_range if tile_range is not None else (0, ntot)
+    if out is None:
+        out = torch.zeros((h, w, 2), dtype=torch.float32, device=ref.device) if (t0, t1) != (0, ntot) else \
+            torch.empty((h, w, 2), dtype=torch.float32, device=ref.device)
+    slot = lib.ma_farneback_workspace_bytes(h, w, T, int(overlap), 1)
+    nb = max(1, min(t1 - t0, FARNEBACK_WORKSPACE_BUDGET // slot))
+    ws = _fb_workspace(ref.device, nb * slot)
+    es = ref.element_size()
+    check(lib.ma_farneback_tiles(mov.data_ptr(), ref.data_ptr(), w * es, _code(ref), h, w, T, int(overlap), int(win),
+                                 int(iters), int(t0), int(t1), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+          "ma_farneback_tiles")
+    return out
+
+
+# --------------------------------------------------------------------------------- DoG / NMI
+def dog_u8(img: torch.Tensor) -> torch.Tensor:
+    _req(img, "image")
+    h, w = img.shape
+    out = torch.empty((h, w), dtype=torch.uint8, device=img.device)
+    ws = _bytes(lib.ma_dog_workspace_bytes(h, w), img.device)
+    check(lib.ma_dog_u8(img.data_ptr(), w * img.element_size(), _code(img), h, w, out.data_ptr(), w, ws.data_ptr(),
+                        _stream()), "ma_dog_u8")
+    return out
+
+
+def nmi_chunks(a: torch.Tensor, b: torch.Tensor, chunk: int) -> torch.Tensor:
+    """Per-chunk NMI (float64 device tensor) of two uint8 label images over raster chunks."""
+    _req(a, "labels a")
+    _req(b, "labels b")
+    if a.dtype != torch.uint8 or b.dtype != torch.uint8 or a.numel() != b.numel():
+        raise ValueError("NMI labels must be uint8 tensors of equal size")
+    n = a.numel()
+    chunk = int(min(chunk, n))
+    nchunks = -(-n // chunk)
+    scores = torch.empty(nchunks, dtype=torch.float64, device=a.device)
+    ws = _bytes(lib.ma_nmi_workspace_bytes(n, chunk), a.device)
+    check(lib.ma_nmi_chunks(a.data_ptr(), b.data_ptr(), n, chunk, scores.data_ptr(), ws.data_ptr(), _stream()),
+          "ma_nmi_chunks")
+    return scores
+
+
+def minmax(img: torch.Tensor) -> torch.Tensor:
+    _req(img, "image")
+    h, w = img.shape
+    out = torch.empty(2, dtype=torch.float32, device=img.device)
+    check(lib.ma_minmax(img.data_ptr(), w * img.element_size(), _code(img), h, w, out.data_ptr(), _stream()), "ma_minmax")
+    return out
+
+
+def zmip_normalize_u8(pages: Sequence[torch.Tensor]) -> torch.Tensor:
+    """z max-projection of same-shape pages followed by min-max normalisation to uint8."""
+    for p in pages:
+        _req(p, "page")
+    h, w = pages[0].shape
+    out = torch.empty((h, w), dtype=torch.uint8, device=pages[0].device)
+    ws = _bytes(lib.ma_zmip_workspace_bytes(h, w, _code(pages[0])), pages[0].device)
+    arr = (ctypes.c_void_p * len(pages))(*[p.data_ptr() for p in pages])
+    check(lib.ma_zmip_normalize_u8(arr, len(pages), w * pages[0].element_size(), _code(pages[0]), h, w, out.data_ptr(), w,
+                                   ws.data_ptr(), _stream()), "ma_zmip_normalize_u8")
+    return out

@@ -1,0 +1,194 @@
+"""OptFlowRegistrator: drop-in for the reference's optflow_reg/optflow_registrator.py:50-274.
+
+Same attribute surface (ref_img, mov_img, num_pyr_lvl, num_iterations, tile_size, overlap,
+use_full_res_img, use_dog), same ValueErrors, same stdout lines, same coarse-to-fine control flow
+-- including the reference's quirks -- but every pixel stays in HBM from
+the first upload to the returned flow: pyramids, DoG images, flows and the similarity histograms
+are device tensors, and per pyramid level only the per-chunk NMI doubles cross to the host.
+
+Inputs may be numpy arrays (result: numpy (H, W, 2) float32, like the reference) or CUDA tensors
+(result: CUDA tensor, for a device-resident hand-off to Warper)."""
+from math import log2
+from typing import List, Tuple
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..shared_modules.img_checks import check_img_dims_match, check_img_is_2d_grey, check_img_is_provided
+from ..shared_modules.similarity_scoring import check_if_higher_similarity
+from .flow_calc import TileFlowCalc
+from .warper import Warper
+
+
+class OptFlowRegistrator:
+    def __init__(self):
+        self._ref_img = np.array([])
+        self._mov_img = np.array([])
+        self.num_pyr_lvl = 4
+        self.num_iterations = 3
+        self.tile_size = 1000
+        self.overlap = 100
+        self.use_full_res_img = False
+        self.use_dog = False
+        self._warper = Warper()
+        self._tile_flow_calc = TileFlowCalc()
+        self.decisions: List[dict] = []  # per level: factor, mi_after, mi_before, better (diagnostic)
+
+    @property
+    def ref_img(self):
+        return self._ref_img
+
+    @ref_img.setter
+    def ref_img(self, img):
+        check_img_is_2d_grey(img, "ref")
+        self._ref_img = img
+
+    @property
+    def mov_img(self):
+        # the reference's getter returns the *reference* image (optflow_registrator.py:72-74); kept
+        return self._ref_img
+
+    @mov_img.setter
+    def mov_img(self, img):
+        check_img_is_2d_grey(img, "mov")
+        self._mov_img = img
+
+    # ------------------------------------------------------------------ helpers
+    def _init_warper(self):
+        self._warper = Warper()
+        self._warper.tile_size = self.tile_size
+        self._warper.overlap = self.overlap
+
+    def _init_tile_flow_calc(self):
+        self._tile_flow_calc = TileFlowCalc()
+        self._tile_flow_calc.tile_size = self.tile_size
+        self._tile_flow_calc.overlap = self.overlap
+        self._tile_flow_calc.num_iter = self.num_iterations
+        self._tile_flow_calc.win_size = self.overlap - (1 - self.overlap % 2)
+
+    def _warp(self, img: torch.Tensor, flow: torch.Tensor) -> torch.Tensor:
+        return ops.warp_tiles(img, flow, self.tile_size, self.overlap)
+
+    def _generate_img_pyr(self, arr: torch.Tensor) -> Tuple[List[torch.Tensor], List[int]]:
+        if self.num_pyr_lvl < 0:
+            raise ValueError("Number of pyramid levels cannot be less than 0")
+        if self.num_pyr_lvl == 0 and not self.use_full_res_img:
+            raise ValueError("Number of pyramid levels is 0 and use_full_res_img is False. "
+                             "Please change one of the parameters")
+        pyramid, factors = [], []
+        cur = arr
+        for lvl in range(self.num_pyr_lvl):
+            factor = 2 ** (lvl + 1)
+            if arr.shape[0] / factor < 100 or arr.shape[1] / factor < 100:
+                break
+            cur = ops.pyr_down(cur)
+            pyramid.append(cur)
+            factors.append(factor)
+        pyramid.reverse()
+        factors.reverse()
+        if self.use_full_res_img:
+            pyramid.append(arr)
+            factors.append(1)
+        return pyramid, factors
+
+    def _upscale_flow_to_full_res(self, flow: torch.Tensor, pyramid_factor: int) -> torch.Tensor:
+        full = tuple(self._full_shape)
+        if abs(flow.shape[0] - full[0]) <= 1:
+            return flow
+        num_lvls = int(log2(pyramid_factor))
+        upscaled = flow
+        for i in range(num_lvls):
+            # the reference restarts from `flow` every pass and does NOT scale by 2 (quirk Q2)
+            dst = full if i == num_lvls - 1 else (2 * flow.shape[0], 2 * flow.shape[1])
+            upscaled = ops.pyr_up_flow(flow, dst, 1.0)
+        return upscaled
+
+    def _merge_list_of_flows(self, flow_list: List[torch.Tensor]) -> torch.Tensor:
+        m_flow = flow_list[0]
+        for f in flow_list[1:]:
+            m_flow = ops.merge_flows_tiles(m_flow, f, self.tile_size, self.overlap)
+        return m_flow
+
+    def get_dog_sigmas(self, pyr_factor: int) -> Tuple[int, int]:
+        if pyr_factor > 16:
+            return 1, 2
+        return {1: (5, 9), 2: (4, 7), 4: (3, 5), 8: (2, 3), 16: (1, 2)}[pyr_factor]
+
+    def dog(self, img, use_it: bool, low_sigma: int = 5, high_sigma: int = 9):
+        """Difference of Gaussians (sigma 5 / 9, 41-tap) -> uint8; identity when use_it is False.
+        An all-zero image yields all-zero labels (the reference returns the zero input itself)."""
+        if not use_it:
+            return img
+        if (low_sigma, high_sigma) != (5, 9):
+            raise NotImplementedError("the device DoG implements the reference's fixed sigmas (5, 9)")
+        if isinstance(img, torch.Tensor):
+            return ops.dog_u8(img)
+        return ops.to_host(ops.dog_u8(ops.to_device(img)))
+
+    # ------------------------------------------------------------------ the hot path
+    def register(self):
+        check_img_is_provided(self._ref_img, "ref")
+        check_img_is_provided(self._mov_img, "mov")
+        check_img_dims_match(self._ref_img, self._mov_img)
+        host_result = not isinstance(self._ref_img, torch.Tensor)
+
+        self._init_tile_flow_calc()
+        self._init_warper()
+        tfc = self._tile_flow_calc
+
+        ref = ops.to_device(self._ref_img)
+        mov = ops.to_device(self._mov_img, ref.device)
+        self._full_shape = tuple(ref.shape)
+        ref_pyr, factors = self._generate_img_pyr(ref)
+        mov_pyr, _ = self._generate_img_pyr(mov)
+        self.decisions = []
+
+        num_lvl = len(factors)
+        for lvl, factor in enumerate(factors):
+            print("Pyramid factor", factor)
+            mov_this_lvl = mov_pyr[lvl]
+            if lvl > 0:
+                mov_this_lvl = self._warp(mov_this_lvl, m_flow)
+            ref_dog = self.dog(ref_pyr[lvl], True)  # needed by the gate in any case
+            tfc.ref_img = ref_dog if self.use_dog else ref_pyr[lvl]
+            tfc.mov_img = self.dog(mov_this_lvl, self.use_dog)
+            this_flow = tfc.calc_flow()
+
+            mov_this_lvl = self._warp(mov_this_lvl, this_flow)
+            is_higher_similarity = check_if_higher_similarity(
+                ref_dog, self.dog(mov_this_lvl, True), self.dog(mov_pyr[lvl], True), self.tile_size)
+            del ref_dog, mov_this_lvl
+            better = any(is_higher_similarity)
+            self.decisions.append(dict(factor=factor, better=better))
+
+            if better:
+                print("    Better alignment than before")
+                if lvl == 0:
+                    if num_lvl > 1:
+                        m_flow = ops.pyr_up_flow(this_flow, mov_pyr[lvl + 1].shape, 2.0)
+                    else:
+                        m_flow = self._upscale_flow_to_full_res(this_flow, factor)
+                elif lvl == num_lvl - 1:
+                    m_flow = self._merge_list_of_flows([m_flow, this_flow])
+                    if not self.use_full_res_img:
+                        m_flow = self._upscale_flow_to_full_res(m_flow, factor)
+                else:
+                    m_flow = self._merge_list_of_flows([m_flow, this_flow])
+                    m_flow = ops.pyr_up_flow(m_flow, mov_pyr[lvl + 1].shape, 2.0)
+                del this_flow
+            else:
+                print("    Worse alignment than before")
+                if lvl == 0:
+                    shape = tuple(mov_pyr[lvl + 1].shape) if num_lvl > 1 else tuple(mov.shape)
+                    m_flow = torch.zeros(shape + (2,), dtype=torch.float32, device=ref.device)
+                elif lvl == num_lvl - 1:
+                    if not self.use_full_res_img:
+                        m_flow = ops.pyr_up_flow(m_flow, mov.shape, 2.0)
+                else:
+                    m_flow = ops.pyr_up_flow(m_flow, mov_pyr[lvl + 1].shape, 4.0)
+
+        del mov_pyr, ref_pyr
+        # no pyramid level at all (image side / 2 < 100 and no full-res): the reference dies with
+        # UnboundLocalError on m_flow (optflow_registrator.py:173); the name lookup below does the same
+        return ops.to_host(m_flow) if host_result else m_flow

@@ -1,0 +1,30 @@
+"""Warper: drop-in for the reference's optflow_reg/warper.py:29-76 on the B200.
+
+`image` (2-D uint8/uint16) and `flow` ((H, W, 2) float32) may be numpy arrays or CUDA tensors.
+`warp()` remaps the image tile by tile exactly like the reference (cv.remap INTER_LINEAR with
+map = tile-local grid - flow, zero outside the tile window) but without materialising tiles:
+one kernel reads the image and flow and writes the stitched result.  Like the reference it
+blanks `image` and `flow` afterwards.  The result is a numpy array when the image was one,
+otherwise a CUDA tensor (device-resident hand-off inside the pipeline)."""
+import numpy as np
+import torch
+
+from .. import ops
+
+
+class Warper:
+    def __init__(self):
+        self.image = np.array([])
+        self.flow = np.array([])
+        self.tile_size = 1000
+        self.overlap = 100
+        self._slicer_info = {}
+
+    def warp(self):
+        host_result = not isinstance(self.image, torch.Tensor)
+        img = ops.to_device(self.image, self.flow.device if isinstance(self.flow, torch.Tensor) else None)
+        flow = ops.to_device(self.flow, img.device)
+        self.image = np.array([])
+        self.flow = np.array([])
+        out = ops.warp_tiles(img, flow, self.tile_size, self.overlap)
+        return ops.to_host(out) if host_result else out

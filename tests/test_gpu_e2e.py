@@ -1,0 +1,98 @@
+"""-m gpu: OptFlowRegistrator / Warper end to end against the oracle's restatement of the reference
+(oracle.reference_flow with the cv2 backend == the unmodified reference, pinned in test_oracle_flow.py)."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_flow as rf
+from tests.util import synth_pair
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    ((700, 820), np.uint16, dict(num_pyr_lvl=2, tile_size=300, overlap=40, use_full_res_img=True, use_dog=True)),
+    ((900, 1300), np.uint8, dict(num_pyr_lvl=3, tile_size=400, overlap=50, use_full_res_img=False)),
+    ((1000, 1000), np.uint16, dict()),
+    ((640, 1210), np.uint16, dict(num_pyr_lvl=1, tile_size=250, overlap=31, use_full_res_img=True, num_iterations=2)),
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_register_and_warp_match_reference(cuda, case):
+    from microaligner_b200 import OptFlowRegistrator, Warper
+    shape, dtype, kw = case
+    ref, mov = synth_pair(shape[0], shape[1], 1, dtype)
+    log = []
+    want_flow = rf.register(ref, mov, be=rf.CvBackend(), log=log, **kw)
+    T, ov = kw.get("tile_size", 1000), kw.get("overlap", 100)
+    want_img = rf.warp(mov, want_flow, T, ov, rf.CvBackend())
+
+    reg = OptFlowRegistrator()
+    for k, v in kw.items():
+        setattr(reg, k, v)
+    reg.ref_img = ref
+    reg.mov_img = mov
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        flow = reg.register()
+    assert isinstance(flow, np.ndarray) and flow.dtype == np.float32 and flow.shape == shape + (2,)
+    assert [d["better"] for d in reg.decisions] == [l["better"] for l in log]
+    epe = np.sqrt(((flow - want_flow) ** 2).sum(-1))
+    # contract: mean EPE <= 0.01 px, max <= 0.1 px; this implementation is bit-exact
+    assert epe.mean() <= 0.01 and epe.max() <= 0.1
+    assert np.array_equal(flow, want_flow), f"flow differs: max EPE {epe.max()}"
+    out = buf.getvalue().splitlines()
+    assert out[0] == f"Pyramid factor {log[0]['factor']}"
+    assert any(l.startswith("    MI score after:") for l in out)
+
+    w = Warper()
+    w.tile_size, w.overlap = T, ov
+    w.image, w.flow = mov, flow
+    img = w.warp()
+    assert img.dtype == mov.dtype and np.array_equal(img, want_img)
+    assert len(w.image) == 0 and len(w.flow) == 0  # inputs are blanked like the reference
+
+
+def test_device_resident_handoff(cuda):
+    from microaligner_b200 import OptFlowRegistrator, Warper
+    ref, mov = synth_pair(600, 500, 2, np.uint16)
+    reg = OptFlowRegistrator()
+    reg.num_pyr_lvl, reg.tile_size, reg.overlap = 2, 200, 30
+    reg.ref_img, reg.mov_img = ref, mov
+    with contextlib.redirect_stdout(io.StringIO()):
+        f_host = reg.register()
+    reg.ref_img, reg.mov_img = torch.from_numpy(ref).cuda(), torch.from_numpy(mov).cuda()
+    with contextlib.redirect_stdout(io.StringIO()):
+        f_dev = reg.register()
+    assert isinstance(f_dev, torch.Tensor) and f_dev.is_cuda
+    assert np.array_equal(f_dev.cpu().numpy(), f_host)
+    w = Warper()
+    w.tile_size, w.overlap = 200, 30
+    w.image, w.flow = torch.from_numpy(mov).cuda(), f_dev
+    out = w.warp()
+    assert isinstance(out, torch.Tensor) and out.dtype == torch.uint16
+
+
+def test_errors(cuda):
+    from microaligner_b200 import OptFlowRegistrator
+    reg = OptFlowRegistrator()
+    with pytest.raises(ValueError, match="No ref image provided"):
+        reg.register()
+    with pytest.raises(ValueError, match="2D grayscale"):
+        reg.ref_img = np.zeros((4, 4, 3), np.uint8)
+    reg.ref_img = np.zeros((300, 300), np.uint8)
+    reg.mov_img = np.zeros((300, 301), np.uint8)
+    with pytest.raises(ValueError, match="different dimensions"):
+        reg.register()
+    reg.mov_img = np.zeros((300, 300), np.uint8)
+    reg.num_pyr_lvl = 0
+    with pytest.raises(ValueError, match="Number of pyramid levels is 0"):
+        reg.register()
+    reg.num_pyr_lvl = 4
+    reg.ref_img = np.zeros((150, 150), np.uint8)
+    reg.mov_img = np.zeros((150, 150), np.uint8)
+    with pytest.raises(UnboundLocalError):
+        reg.register()
