@@ -1,0 +1,310 @@
+"""bench.py -- Mpixel/s registered (Farneback flow + warp), BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--size S]
+
+A step = OptFlowRegistrator.register() + Warper.warp() on one synthetic uint16 pair (BASELINE.json
+configs[1]: 20000 x 20000, 4 pyramid levels + full resolution, 3 iterations, 1000-px tiles, 100-px
+overlap, no DoG prefilter).  One JSON line is printed by rank 0:
+
+  value      whole-job Mpx/s with ref/mov already resident in HBM (CUDA events, max over ranks)
+  e2e        the same step through the drop-in numpy API: page-locked host arrays in, host arrays out
+             (H2D of ref+mov, D2H of the flow, H2D of image+flow for Warper, D2H of the warped image)
+  roofline   dominant kernel, timed live with CUDA events inside the library during the timed steps
+  cpu_baseline  the oracle port of the reference (same cv2 / sklearn calls, all host threads) on a
+             bounded crop of the same pair (rank 0, N=1 only)
+
+--impl reference times that CPU path alone (rank 0), same metric/unit/config, K bounded-sample steps.
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PARAMS = dict(num_pyr_lvl=4, num_iterations=3, tile_size=1000, overlap=100, use_full_res_img=True, use_dog=False)
+
+# algorithmic HBM bytes per unit (unit = tile-pixel for fb_*, pixel otherwise; u16 input)
+ALG_BYTES = {
+    "fb_polyexp": 44.0, "fb_update0": 60.0, "fb_blur_v": 20.0,
+    "fb_blur_h": None,  # 68 per non-final iteration (R0 20 + R1 20 + M 20 + flow 8), 8 on the final one
+    "warp_tiles": 12.0, "tile_max": 16.0, "merge_tiles": 24.0, "pyrdown": 2.5, "pyrup_flow": 10.0,
+    "minmax": 2.0, "dog_row": 2.0, "dog_col": 4.0, "dog_quant": 5.0, "nmi_hist": 2.0,
+}
+# FP32 lane-instructions per unit of the two FP32-bound kernels: 5 planes x (1 + 3 m), m = 49
+FP32_INSTR = {"fb_blur_v": 5 * (1 + 3 * 49), "fb_blur_h": 5 * (1 + 3 * 49)}
+# dram__bytes_read.sum + dram__bytes_write.sum per unit from the committed ncu --set full capture (profiles/)
+NCU_TRAFFIC_PER_UNIT = {}
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        busy = [v for v in sm if v > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+# ----------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_step(ref, mov, workers):
+    from oracle import reference_flow as rf  # the one place bench.py executes oracle/: the CPU baseline
+    be = rf.CvBackend(workers=workers)
+    t = time.perf_counter()
+    flow = rf.register(ref, mov, be=be, **PARAMS)
+    rf.warp(mov, flow, PARAMS["tile_size"], PARAMS["overlap"], be)
+    return time.perf_counter() - t
+
+
+def cpu_sample(size, sample):
+    from benchdata import synth_pair_large
+    s = min(size, sample)
+    return synth_pair_large(s, s, seed=0)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import cv2
+    workers = os.cpu_count() or 1
+    cv2.setNumThreads(1)
+    ref, mov = cpu_sample(args.size, args.cpu_sample)
+    px = ref.size
+    for _ in range(args.warmup):
+        cpu_reference_step(ref[:1200, :1200].copy(), mov[:1200, :1200].copy(), workers)
+    ts = [cpu_reference_step(ref, mov, workers) for _ in range(args.steps)]
+    t = float(np.mean(ts))
+    v = px / t / 1e6
+    sample = f"{ref.shape[0]}x{ref.shape[1]} crop of the {args.size}x{args.size} pair, same parameters"
+    print(json.dumps({
+        "impl": "reference", "metric": "Mpixel/s registered (Farneback flow + warp)", "value": v, "unit": "Mpx/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, sample),
+        "cpu_baseline": {"value": v, "unit": "Mpx/s", "cores": workers, "kind": "port", "sample": sample,
+                         "cv2": cv2.__version__},
+        "e2e": {"value": v, "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args, sample=None):
+    c = {"workload": f"single {args.size}x{args.size} uint16 synthetic pair, tiled optical flow + warp",
+         "params": PARAMS, "l2": "inputs (2 x %.1f GB) larger than the 126 MB L2" % (args.size * args.size * 2 / 1e9)}
+    if sample:
+        c["sample"] = sample
+    return c
+
+
+# ----------------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from benchdata import synth_pair_large
+    from microaligner_b200 import OptFlowRegistrator, Warper, _lib, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        from microaligner_b200 import parallel
+        parallel.init(dist.group.WORLD)
+
+    S = args.size
+    ref_h = torch.empty((S, S), dtype=torch.uint16, pin_memory=True).numpy()
+    mov_h = torch.empty((S, S), dtype=torch.uint16, pin_memory=True).numpy()
+    synth_pair_large(S, S, seed=0, out=(ref_h, mov_h))
+    ref_d, mov_d = torch.from_numpy(ref_h).to(dev), torch.from_numpy(mov_h).to(dev)
+
+    reg, wrp = OptFlowRegistrator(), Warper()
+    for k, v in PARAMS.items():
+        setattr(reg, k, v)
+    wrp.tile_size, wrp.overlap = PARAMS["tile_size"], PARAMS["overlap"]
+
+    def step_device():
+        reg.ref_img, reg.mov_img = ref_d, mov_d
+        flow = reg.register()
+        wrp.image, wrp.flow = mov_d, flow
+        return wrp.warp()
+
+    def step_host():
+        reg.ref_img, reg.mov_img = ref_h, mov_h
+        flow = reg.register()
+        wrp.image, wrp.flow = mov_h, flow
+        return wrp.warp()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            out = fn()
+        b.record()
+        barrier()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, out
+
+    with quiet():
+        for _ in range(args.warmup):
+            step_device()
+        launches0 = _lib.lib.ma_launch_count()
+        _lib.lib.ma_profile_reset()
+        _lib.lib.ma_profile_enable(1)
+        with ClockSampler(local) as clk:
+            ms_dev, _ = timed(step_device, args.steps)
+        _lib.lib.ma_profile_enable(0)
+        launches = _lib.lib.ma_launch_count() - launches0
+        prof = _lib.profile_summary()
+        # end-to-end through the numpy API (page-locked host arrays)
+        for _ in range(max(1, min(args.warmup, 2))):
+            step_host()
+        ms_e2e, out_h = timed(step_host, args.steps)
+    px = S * S
+    value = px / (ms_dev * 1e-3) / 1e6
+    e2e_val = px / (ms_e2e * 1e-3) / 1e6
+    img_b, flow_b = px * 2, px * 8
+    h2d = 2 * img_b + img_b + flow_b   # register(ref, mov) + Warper(image, flow)
+    d2h = flow_b + img_b               # flow returned by register(), warped image
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    clocks = clk.summary()
+    peak, peak_src = measured_hbm_peak()
+    N = PARAMS["num_iterations"]
+    kernels = {}
+    for name, (ms, n, units) in prof.items():
+        kernels[name] = {"ms_per_step": ms / args.steps, "launches_per_step": n / args.steps, "units_per_step": units / args.steps}
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
+    roofline = None
+    if dom:
+        k = kernels[dom]
+        bpu = ALG_BYTES.get(dom)
+        if dom == "fb_blur_h":
+            bpu = (68.0 * (N - 1) + 8.0) / N
+        avg_ms = k["ms_per_step"] / k["launches_per_step"]
+        units_per_launch = k["units_per_step"] / k["launches_per_step"]
+        achieved = (bpu or 0) * units_per_launch / (avg_ms * 1e-3) / 1e9
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "peak_source": peak_src, "alg_bytes_per_unit": bpu, "units_per_launch": units_per_launch,
+                    "avg_launch_ms": avg_ms, "share_of_step": k["ms_per_step"] / ms_dev,
+                    "traffic": (NCU_TRAFFIC_PER_UNIT[dom] * units_per_launch) if dom in NCU_TRAFFIC_PER_UNIT else None}
+        if dom in FP32_INSTR and clocks.get("sm_mhz"):
+            fp_peak = 148 * 128 * clocks["sm_mhz"] * 1e6
+            fp_ach = FP32_INSTR[dom] * units_per_launch / (avg_ms * 1e-3)
+            roofline["fp32_issue"] = {"note": "kernel is FP32-issue bound, not HBM bound (DESIGN.md)", "achieved_ginstr_s": fp_ach / 1e9,
+                                      "peak_ginstr_s": fp_peak / 1e9, "frac": fp_ach / fp_peak, "at_sm_mhz": clocks["sm_mhz"]}
+    line = {
+        "metric": "Mpixel/s registered (Farneback flow + warp)", "value": value, "unit": "Mpx/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
+        "e2e": {"value": e2e_val, "unit": "Mpx/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "OptFlowRegistrator.register() + Warper.warp() on page-locked numpy arrays"},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        "kernels": {k: {kk: round(vv, 4) for kk, vv in v.items()} for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms_per_step"])},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        import cv2
+        cv2.setNumThreads(1)
+        workers = os.cpu_count() or 1
+        s = min(S, args.cpu_sample)
+        cref, cmov = np.ascontiguousarray(ref_h[:s, :s]), np.ascontiguousarray(mov_h[:s, :s])
+        with quiet():
+            t = cpu_reference_step(cref, cmov, workers)
+        line["cpu_baseline"] = {"value": s * s / t / 1e6, "unit": "Mpx/s", "cores": workers, "kind": "port", "seconds": t,
+                                "sample": f"{s}x{s} crop of the same pair, same parameters, one pass", "cv2": cv2.__version__}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=20000)
+    ap.add_argument("--cpu-sample", type=int, default=4000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -101,6 +101,17 @@ int ma_zmip_normalize_u8(const void* const* pages_host, int n_pages, size_t pitc
 /* global min/max of an image as two floats (device, out2[0]=min, out2[1]=max). */
 int ma_minmax(const void* src, size_t pitch, int dtype, int h, int w, float* out2, void* stream);
 
+/* ---- accounting: kernels launched by this library so far, and an optional per-kernel profiler that
+ * brackets every launch with CUDA events on the launching stream (off by default; bench.py turns it on
+ * for the timed region).  ma_profile_read drains pending events (synchronises on them). `units` is the
+ * number of pixels / tile-pixels the launches processed. */
+long long ma_launch_count(void);
+int ma_profile_kernels(void);
+const char* ma_profile_kernel_name(int id);
+void ma_profile_enable(int on);
+void ma_profile_reset(void);
+int ma_profile_read(int id, double* total_ms, long long* launches, double* units);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,7 +43,24 @@ PROTOTYPES = {
     "ma_zmip_normalize_u8": (c_int, [ctypes.POINTER(c_void_p), c_int, c_size_t, c_int, c_int, c_int, c_void_p, c_size_t,
                                      c_void_p, c_void_p]),
     "ma_minmax": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "ma_launch_count": (ctypes.c_longlong, []),
+    "ma_profile_kernels": (c_int, []),
+    "ma_profile_kernel_name": (c_char_p, [c_int]),
+    "ma_profile_enable": (None, [c_int]),
+    "ma_profile_reset": (None, []),
+    "ma_profile_read": (c_int, [c_int, ctypes.POINTER(c_double), ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(c_double)]),
 }
+
+
+def profile_summary():
+    """{kernel name: (total ms, launches, units)} accumulated since ma_profile_reset()."""
+    out = {}
+    for i in range(lib.ma_profile_kernels()):
+        ms, n, u = c_double(), ctypes.c_longlong(), c_double()
+        lib.ma_profile_read(i, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(u))
+        if n.value:
+            out[lib.ma_profile_kernel_name(i).decode()] = (ms.value, n.value, u.value)
+    return out
 
 for _name, (_res, _args) in PROTOTYPES.items():
     _fn = getattr(lib, _name)  # AttributeError here = header and library out of sync

@@ -283,13 +283,14 @@ extern "C" int ma_minmax(const void* src, size_t pitch, int dtype, int h, int w,
     cudaStream_t s = (cudaStream_t)stream;
     // out2 doubles as the key scratch (2 x 4 bytes), converted in place at the end
     unsigned* keys = (unsigned*)out2;
-    init_minmax_keys<<<1, 32, 0, s>>>(keys, 1);
+    { KernelScope ks(K_SMALL, s); init_minmax_keys<<<1, 32, 0, s>>>(keys, 1); }
     dim3 grid(std::min(ceil_div(w, 256), 8), std::min(h, 1184));
+    { KernelScope ks(K_MINMAX, s, (double)h * w);
     if (dtype == MA_U8) minmax_kernel<uint8_t><<<grid, 256, 0, s>>>((const uint8_t*)src, pitch, h, w, keys);
     else if (dtype == MA_U16) minmax_kernel<uint16_t><<<grid, 256, 0, s>>>((const uint16_t*)src, pitch, h, w, keys);
     else if (dtype == MA_F32) minmax_kernel<float><<<grid, 256, 0, s>>>((const float*)src, pitch, h, w, keys);
-    else return invalid("ma_minmax: bad dtype");
-    keys_to_float_kernel<<<1, 1, 0, s>>>(keys, out2);
+    else return invalid("ma_minmax: bad dtype"); }
+    { KernelScope ks(K_SMALL, s); keys_to_float_kernel<<<1, 1, 0, s>>>(keys, out2); }
     MA_LAUNCH_CHECK("minmax_kernel");
     return MA_OK;
 }
@@ -313,18 +314,19 @@ extern "C" int ma_dog_u8(const void* src, size_t src_pitch, int dtype, int h, in
     static DogTaps taps;
     static bool taps_ready = false;
     if (!taps_ready) { make_dog_taps(taps); taps_ready = true; }
-    init_minmax_keys<<<1, 32, 0, s>>>(keys, 2);
+    double px = (double)h * w;
+    { KernelScope ks(K_SMALL, s); init_minmax_keys<<<1, 32, 0, s>>>(keys, 2); }
     dim3 mg(std::min(ceil_div(w, 256), 8), std::min(h, 1184));
     dim3 rg(ceil_div(w, DOG_HW), ceil_div(h, DOG_HROWS)), rb(DOG_HT, DOG_HROWS);
     if (dtype == MA_U8) {
-        minmax_kernel<uint8_t><<<mg, 256, 0, s>>>((const uint8_t*)src, src_pitch, h, w, keys);
-        dog_row_kernel<uint8_t><<<rg, rb, 0, s>>>((const uint8_t*)src, src_pitch, h, w, keys, A5, A9, wp, taps);
+        { KernelScope ks(K_MINMAX, s, px); minmax_kernel<uint8_t><<<mg, 256, 0, s>>>((const uint8_t*)src, src_pitch, h, w, keys); }
+        { KernelScope ks(K_DOG_ROW, s, px); dog_row_kernel<uint8_t><<<rg, rb, 0, s>>>((const uint8_t*)src, src_pitch, h, w, keys, A5, A9, wp, taps); }
     } else {
-        minmax_kernel<uint16_t><<<mg, 256, 0, s>>>((const uint16_t*)src, src_pitch, h, w, keys);
-        dog_row_kernel<uint16_t><<<rg, rb, 0, s>>>((const uint16_t*)src, src_pitch, h, w, keys, A5, A9, wp, taps);
+        { KernelScope ks(K_MINMAX, s, px); minmax_kernel<uint16_t><<<mg, 256, 0, s>>>((const uint16_t*)src, src_pitch, h, w, keys); }
+        { KernelScope ks(K_DOG_ROW, s, px); dog_row_kernel<uint16_t><<<rg, rb, 0, s>>>((const uint16_t*)src, src_pitch, h, w, keys, A5, A9, wp, taps); }
     }
-    dog_col_kernel<<<dim3(ceil_div(w, 32), ceil_div(h, 8 * DOG_VR)), 256, 0, s>>>(A5, A9, wp, h, w, D, keys + 2, taps);
-    dog_quant_kernel<<<dim3(ceil_div(ceil_div(w, 4), 256), h), 256, 0, s>>>(D, wp, h, w, keys + 2, dst, dst_pitch);
+    { KernelScope ks(K_DOG_COL, s, px); dog_col_kernel<<<dim3(ceil_div(w, 32), ceil_div(h, 8 * DOG_VR)), 256, 0, s>>>(A5, A9, wp, h, w, D, keys + 2, taps); }
+    { KernelScope ks(K_DOG_QUANT, s, px); dog_quant_kernel<<<dim3(ceil_div(ceil_div(w, 4), 256), h), 256, 0, s>>>(D, wp, h, w, keys + 2, dst, dst_pitch); }
     MA_LAUNCH_CHECK("dog kernels");
     return MA_OK;
 }
@@ -345,14 +347,14 @@ extern "C" int ma_zmip_normalize_u8(const void* const* pages_host, int n_pages, 
     unsigned* keys = (unsigned*)workspace;
     void* mip = (char*)workspace + 256;
     int mp = pad4(w);
-    init_minmax_keys<<<1, 32, 0, s>>>(keys, 1);
+    { KernelScope ks(K_SMALL, s); init_minmax_keys<<<1, 32, 0, s>>>(keys, 1); }
     dim3 grid(ceil_div(w, 256), h), zgrid(ceil_div(w, 256), std::min(h, 2048));
     if (dtype == MA_U8) {
-        zmip_kernel<uint8_t><<<zgrid, 256, 0, s>>>(pp, n_pages, pitch, h, w, (uint8_t*)mip, mp, keys);
-        norm_u8_kernel<uint8_t><<<grid, 256, 0, s>>>((const uint8_t*)mip, mp, h, w, keys, dst, dst_pitch);
+        { KernelScope ks(K_ZMIP, s, (double)h * w); zmip_kernel<uint8_t><<<zgrid, 256, 0, s>>>(pp, n_pages, pitch, h, w, (uint8_t*)mip, mp, keys); }
+        { KernelScope ks(K_NORM_U8, s, (double)h * w); norm_u8_kernel<uint8_t><<<grid, 256, 0, s>>>((const uint8_t*)mip, mp, h, w, keys, dst, dst_pitch); }
     } else {
-        zmip_kernel<uint16_t><<<zgrid, 256, 0, s>>>(pp, n_pages, pitch, h, w, (uint16_t*)mip, mp, keys);
-        norm_u8_kernel<uint16_t><<<grid, 256, 0, s>>>((const uint16_t*)mip, mp, h, w, keys, dst, dst_pitch);
+        { KernelScope ks(K_ZMIP, s, (double)h * w); zmip_kernel<uint16_t><<<zgrid, 256, 0, s>>>(pp, n_pages, pitch, h, w, (uint16_t*)mip, mp, keys); }
+        { KernelScope ks(K_NORM_U8, s, (double)h * w); norm_u8_kernel<uint16_t><<<grid, 256, 0, s>>>((const uint16_t*)mip, mp, h, w, keys, dst, dst_pitch); }
     }
     MA_LAUNCH_CHECK("zmip kernels");
     return MA_OK;

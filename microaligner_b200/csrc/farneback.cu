@@ -23,30 +23,30 @@
 #include <cmath>
 #include <vector>
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace ma {
 
-constexpr int kMaxM = 96;         // ring capacity 256 >= step 64 + 2*m
-constexpr int kRing = 256;        // virtual rows/cols kept in the ring (power of two)
-constexpr int kStep = 64;         // outputs per sweep step along the convolution axis
+constexpr int kMaxM = 96;         // TMA box rows 64 + 2*m <= 256
+constexpr int kStep = 64;         // outputs per CTA along the convolution axis (H pass; V pass: 64 or 128)
 constexpr int kR = 8;             // outputs per thread along the convolution axis
-constexpr int kLanes = 32;        // strip width across the convolution axis
-constexpr int kHPitch = 33;       // H-pass ring pitch (floats): conflict-free transposed stores
 
 struct FbConsts {
     float g0, g1, xg1, xxg1;            // polyexp taps: centre g[0], side g[1], x*g, x*x*g at +1
     double ig11, ig03, ig33, ig55;      // inverse Gram constants
     int m;                              // blur half width
-    float k[kMaxM + 1];                 // blur taps
+    float2 negzero2;                    // {-0.f, -0.f}, see mul2()
+    float2 k2[kMaxM + 1];               // blur taps, duplicated {k, k} for the packed f32x2 multiply
 };
 
 struct FbBatch {
     TileGeom g;
     int tile0;        // first tile (row-major index) of this batch
     int ntiles;       // tiles in this batch
-    int Sp;           // plane row pitch in floats
-    size_t plane;     // floats per plane (Sh * Sp)
-    float* ws;        // workspace base: per slot 20 planes [R0 x5][R1 x5][M x5][V x5]
+    int Sp;           // row pitch (floats) of the R0 / R1 / M planes ([y][x])
+    int SpT;          // row pitch (floats) of the transposed V planes ([x][y])
+    size_t plane;     // floats per plane = max(Sh * Sp, Sw * SpT)
+    float* ws;        // workspace base: per slot 20 planes [R0 x5][R1 x5][M x5][V^T x5]
 };
 
 __device__ __forceinline__ float* slot_plane(const FbBatch& b, int slot, int which /*0 R0,1 R1,2 M,3 V*/, int c) {
@@ -198,156 +198,249 @@ __global__ void __launch_bounds__(256) fb_update0_kernel(FbBatch b) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3 core: symmetric (2m+1)-tap convolution of 8 consecutive outputs per thread, OpenCV order.
-// `ring` points at this thread's lane; element for virtual index v is ring[(v & (kRing-1)) * pitch].
-// Outputs v0 .. v0+7.  Two 8-wide register windows slide in opposite directions; with the loop
-// unrolled by 8 all register indices are static.
+// K3 core: symmetric (2m+1)-tap convolution, OpenCV order  s = c*k0; s += (a[+i] + a[-i]) * k[i].
+//
+// The tile of inputs sits in shared memory as rows of 64 floats (256 B, written by one TMA box load);
+// the convolution runs along the row index.  A thread owns the two adjacent columns (2*lane, 2*lane+1)
+// as one packed f32x2 value and produces 8 consecutive outputs along the convolution axis, keeping
+// two 8-deep sliding windows in registers, so one step costs 2 LDS.64 for 8 x (FADD2, FMUL2, FADD2).
+// Packed FADD2 issues at twice the scalar lane rate on sm_100 (measured, scripts/microbench), which
+// makes the separately-rounded add/mul/add sequence as cheap as a fused scalar FMA formulation.
+// With the loop unrolled by 8 every register index is static.
 // ------------------------------------------------------------------------------------------------
-template <int PITCH>
-__device__ __forceinline__ void conv8_sym(const float* __restrict__ ring, int v0, const FbConsts& cst, float (&acc)[kR]) {
-    float wp[kR], wm[kR];
-    const float k0 = cst.k[0];
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// a*b rounded once.  ptxas contracts a mul.rn.f32x2 feeding an add.rn.f32x2 into one FFMA2 (observed
+// in SASS, also with a literal -0 addend), which would break parity with OpenCV's unfused arithmetic.
+// The product is therefore an explicit fma with a -0 addend that arrives as a *runtime* value
+// (FbConsts::negzero2): x*k + (-0) == x*k exactly, and the following add cannot be merged into it.
+__device__ __forceinline__ u64 mul2(u64 a, u64 b, u64 negzero) {
+    u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(negzero));
+    return r;
+}
+__device__ __forceinline__ u64 pack2(float x, float y) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+__device__ __forceinline__ float2 unpack2(u64 v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+
+constexpr int kRowF = 64;            // floats per shared-memory row (one TMA box row)
+constexpr int kRowU = kRowF / 2;     // packed pairs per row
+
+// `centre` -> this thread's pair in the row holding the centre tap of output 0; outputs 0..7 are the
+// next rows.  k2[i] = {k[i], k[i]}.
+__device__ __forceinline__ void conv8x2(const u64* __restrict__ centre, int m, const float2* __restrict__ k2, u64 nz, u64 (&acc)[kR]) {
+    u64 wp[kR], wm[kR];
+    const u64 k0 = *reinterpret_cast<const u64*>(&k2[0]);
 #pragma unroll
     for (int j = 0; j < kR; ++j) {
-        float c = ring[((v0 + j) & (kRing - 1)) * PITCH];
+        u64 c = centre[j * kRowU];
         wp[j] = c;
         wm[j] = c;
-        acc[j] = __fmul_rn(c, k0);
+        acc[j] = mul2(c, k0, nz);
     }
-    const int m = cst.m;
-    // invariant before step i: wp[(j+i-1)&7] = in[v0+j+i-1], wm[(j-i+1)&7] = in[v0+j-i+1]
-    for (int i0 = 1; i0 <= m; i0 += kR) {
+    const u64* pp = centre + kR * kRowU;   // row of in[+7 + i] for i = 1
+    const u64* pm = centre - kRowU;        // row of in[-i] for i = 1
+    int i = 1;
+    // before step i: in[j+i-1] lives in wp[(j+i-1)&7], in[j-i+1] in wm[(j-i+1)&7]; i = 8g+1+s
+#pragma unroll 1
+    for (; i + kR - 1 <= m; i += kR) {
 #pragma unroll
         for (int s = 0; s < kR; ++s) {
-            int i = i0 + s;
-            if (i <= m) {  // warp-uniform
-                float ki = cst.k[i];
-                // (i0 - 1) is a multiple of 8, so (x + i) & 7 == (x + s + 1) & 7: static indices
-                wp[(kR - 1 + s + 1) & 7] = ring[((v0 + kR - 1 + i) & (kRing - 1)) * PITCH];
-                wm[(8 * kR - s - 1) & 7] = ring[((v0 - i) & (kRing - 1)) * PITCH];
+            wp[s] = pp[s * kRowU];
+            wm[(63 - s) & 7] = pm[-s * kRowU];
+            const u64 kk = *reinterpret_cast<const u64*>(&k2[i + s]);
 #pragma unroll
-                for (int j = 0; j < kR; ++j) {
-                    float t = __fadd_rn(wp[(j + s + 1) & 7], wm[(j + 8 * kR - s - 1) & 7]);
-                    acc[j] = __fadd_rn(acc[j], __fmul_rn(t, ki));
-                }
-            }
+            for (int j = 0; j < kR; ++j) acc[j] = add2(acc[j], mul2(add2(wp[(j + s + 1) & 7], wm[(j + 63 - s) & 7]), kk, nz));
+        }
+        pp += kR * kRowU;
+        pm -= kR * kRowU;
+    }
+#pragma unroll
+    for (int s = 0; s < kR - 1; ++s) {
+        if (i + s <= m) {  // warp-uniform tail (m mod 8 steps)
+            wp[s] = pp[s * kRowU];
+            wm[(63 - s) & 7] = pm[-s * kRowU];
+            const u64 kk = *reinterpret_cast<const u64*>(&k2[i + s]);
+#pragma unroll
+            for (int j = 0; j < kR; ++j) acc[j] = add2(acc[j], mul2(add2(wp[(j + s + 1) & 7], wm[(j + 63 - s) & 7]), kk, nz));
         }
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// K3a: vertical pass M -> V.  CTA = strip of 32 columns of one plane of one tile, swept downwards in
-// steps of 64 rows (8 warps x 8 rows); lane <-> column (coalesced 128-byte rows, conflict-free smem).
-// grid = (ceil(Sw/32), nseg, ntiles*5)
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) fb_blur_v_kernel(FbBatch b, const __grid_constant__ FbConsts cst, int rows_per_seg) {
-    __shared__ float ring[kRing * kLanes];
-    const int Sh = b.g.Sh, Sw = b.g.Sw, Sp = b.Sp, m = cst.m;
-    int slot = blockIdx.z / 5, c = blockIdx.z % 5;
-    const float* __restrict__ src = slot_plane(b, slot, 2, c);
-    float* __restrict__ dst = slot_plane(b, slot, 3, c);
-    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int x = blockIdx.x * kLanes + lane;
-    int xc = min(x, Sw - 1);
-    int ybeg = blockIdx.y * rows_per_seg, yend = min(ybeg + rows_per_seg, Sh);
-    int loaded = ybeg - m;  // next virtual row to load
-    for (int y0 = ybeg; y0 < yend; y0 += kStep) {
-        int need = min(y0 + kStep, yend) + m;  // exclusive
-        __syncthreads();                       // previous step finished reading the slots we overwrite
-        for (int v = loaded + warp; v < need; v += 8) {
-            int yy = min(max(v, 0), Sh - 1);
-            ring[(v & (kRing - 1)) * kLanes + lane] = __ldg(src + (size_t)yy * Sp + xc);
-        }
-        loaded = need;
-        __syncthreads();
-        int v0 = y0 + warp * kR;
-        if (v0 < yend) {
-            float acc[kR];
-            conv8_sym<kLanes>(ring + lane, v0, cst, acc);
-            if (x < Sw) {
-#pragma unroll
-                for (int j = 0; j < kR; ++j)
-                    if (v0 + j < yend) dst[(size_t)(v0 + j) * Sp + x] = acc[j];
-            }
-        }
+// replicate the first / last valid row of the box into the rows TMA zero-filled outside [0, n)
+// (OpenCV clamps rows / replicates columns at the tile edge).  v_first = coordinate of box row 0.
+__device__ __forceinline__ void replicate_edges(float* buf, int rows, int v_first, int n) {
+    if (v_first >= 0 && v_first + rows <= n) return;   // CTA-uniform
+    const int r_lo = -v_first, r_hi = n - 1 - v_first; // box rows of coordinate 0 and n-1
+    for (int p = threadIdx.x; p < rows * kRowF; p += blockDim.x) {
+        int r = p / kRowF, c = p % kRowF;
+        if (r < r_lo) buf[p] = buf[r_lo * kRowF + c];
+        else if (r > r_hi) buf[p] = buf[r_hi * kRowF + c];
     }
+    fence_proxy_async();
+    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3b: horizontal pass + solve + (UpdateMatrices | final scatter).  CTA = strip of 32 rows of one
-// tile, all 5 planes, swept rightwards in steps of 64 columns (8 warps x 8 columns); lane <-> row
-// for the convolution (ring stored transposed, pitch 33), lane <-> column for the global-memory
-// phases so every HBM access is coalesced.
-// grid = (ceil(Sh/32), nseg, ntiles)
+// K3a: vertical pass M -> V^T.  CTA = 64 columns x OUT rows of one plane of one tile.  One TMA box
+// (64 x (OUT + 2m) floats) lands the inputs; lanes <-> column pairs; the OUT x 64 result block is
+// transposed through shared memory and written as rows of V^T (so that the horizontal pass is the
+// same kernel shape with coalesced, TMA-friendly rows).
+// grid = (ceil(Sw/64), ceil(Sh/OUT), ntiles*5), dynamic smem = (OUT + 2m) * 256 B
 // ------------------------------------------------------------------------------------------------
-constexpr size_t kBlurHSmem = (size_t)5 * kRing * kHPitch * sizeof(float) + (size_t)kLanes * kStep * sizeof(float2);
-
-__global__ void __launch_bounds__(256, 1) fb_blur_h_kernel(FbBatch b, const __grid_constant__ FbConsts cst, int cols_per_seg,
-                                                            int last_iter, float2* __restrict__ flow_out) {
-    extern __shared__ __align__(16) float smem[];
-    float* ring = smem;                                             // [5][kRing][33]
-    float2* fl = (float2*)(smem + 5 * kRing * kHPitch);             // [32 rows][64 cols]
-    const TileGeom& g = b.g;
-    const int Sh = g.Sh, Sw = g.Sw, Sp = b.Sp, m = cst.m;
-    int slot = blockIdx.z;
-    const float* __restrict__ V = slot_plane(b, slot, 3, 0);
-    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int ybase = blockIdx.x * kLanes;
-    int xbeg = blockIdx.y * cols_per_seg, xend = min(xbeg + cols_per_seg, Sw);
-    int loaded = xbeg - m;
-    int tile = b.tile0 + slot;
-    int ti = tile / g.nx, tj = tile % g.nx;
-    for (int x0 = xbeg; x0 < xend; x0 += kStep) {
-        int need = min(x0 + kStep, xend) + m;
-        __syncthreads();
-        // load virtual columns [loaded, need) for 32 rows x 5 planes; thread <-> column (coalesced)
-        int ncol = need - loaded;
-        for (int p = threadIdx.x; p < ncol * kLanes * 5; p += 256) {
-            int cidx = p % ncol, rest = p / ncol;
-            int r = rest % kLanes, c = rest / kLanes;
-            int v = loaded + cidx;
-            int xx = min(max(v, 0), Sw - 1), yy = min(ybase + r, Sh - 1);
-            ring[(c * kRing + (v & (kRing - 1))) * kHPitch + r] = __ldg(V + c * b.plane + (size_t)yy * Sp + xx);
-        }
-        loaded = need;
-        __syncthreads();
-        int v0 = x0 + warp * kR;
-        if (v0 < xend) {
-            float a0[kR], a1[kR], a2[kR], a3[kR], a4[kR];
-            conv8_sym<kHPitch>(ring + 0 * kRing * kHPitch + lane, v0, cst, a0);
-            conv8_sym<kHPitch>(ring + 1 * kRing * kHPitch + lane, v0, cst, a1);
-            conv8_sym<kHPitch>(ring + 2 * kRing * kHPitch + lane, v0, cst, a2);
-            conv8_sym<kHPitch>(ring + 3 * kRing * kHPitch + lane, v0, cst, a3);
-            conv8_sym<kHPitch>(ring + 4 * kRing * kHPitch + lane, v0, cst, a4);
+template <int OUT>
+__global__ void __launch_bounds__(256) fb_blur_v_kernel(const __grid_constant__ CUtensorMap mapM, FbBatch b,
+                                                        const __grid_constant__ FbConsts cst) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t bar;
+    const int Sh = b.g.Sh, Sw = b.g.Sw, m = cst.m;
+    const int slot = blockIdx.z / 5, c = blockIdx.z % 5;
+    const int x0 = blockIdx.x * kRowF, y0 = blockIdx.y * OUT;
+    const int rows = OUT + 2 * m;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, rows * kRowF * sizeof(float));
+        tma_load_3d(smem, &mapM, x0, y0 - m, slot * 20 + 10 + c, &bar);
+    }
+    mbar_wait(&bar, 0);
+    replicate_edges(smem, rows, y0 - m, Sh);
+    const u64 nz = *reinterpret_cast<const u64*>(&cst.negzero2);
+    u64 acc[OUT / 64][kR];
+#pragma unroll
+    for (int grp = 0; grp < OUT / 64; ++grp) {
+        int o0 = grp * 64 + warp * kR;
+        if (y0 + o0 < Sh) conv8x2(reinterpret_cast<const u64*>(smem) + (o0 + m) * kRowU + lane, m, cst.k2, nz, acc[grp]);
+    }
+    __syncthreads();  // everyone is done reading the inputs: reuse the buffer as the transpose stage
+    constexpr int SP = OUT + 1;
+    float* stage = smem;  // [64 x][OUT + 1]
+#pragma unroll
+    for (int grp = 0; grp < OUT / 64; ++grp) {
+        int o0 = grp * 64 + warp * kR;
+        if (y0 + o0 < Sh) {
 #pragma unroll
             for (int j = 0; j < kR; ++j) {
-                double g11 = a0[j], g12 = a1[j], g22 = a2[j], h1 = a3[j], h2 = a4[j];
-                double det = __dadd_rn(__dsub_rn(__dmul_rn(g11, g22), __dmul_rn(g12, g12)), 1e-3);
-                double idet = __ddiv_rn(1.0, det);
-                float fx = (float)__dmul_rn(__dsub_rn(__dmul_rn(g11, h2), __dmul_rn(g12, h1)), idet);
-                float fy = (float)__dmul_rn(__dsub_rn(__dmul_rn(g22, h1), __dmul_rn(g12, h2)), idet);
-                fl[lane * kStep + warp * kR + j] = make_float2(fx, fy);
+                float2 v = unpack2(acc[grp][j]);
+                stage[(2 * lane) * SP + o0 + j] = v.x;
+                stage[(2 * lane + 1) * SP + o0 + j] = v.y;
             }
         }
-        __syncthreads();
-        // epilogue: thread <-> column
-        int cx = threadIdx.x & 63;
-        int x = x0 + cx;
-        if (x < xend) {
-            for (int r = threadIdx.x >> 6; r < kLanes; r += 4) {
-                int y = ybase + r;
-                if (y >= Sh) break;
-                float2 f = fl[r * kStep + cx];
-                if (last_iter) {
-                    int cy = y - g.ov, cxx = x - g.ov;
-                    if ((unsigned)cy < (unsigned)g.Th && (unsigned)cxx < (unsigned)g.Tw) {
-                        int gy = ti * g.Th + cy, gx = tj * g.Tw + cxx;
-                        if (gy < g.h && gx < g.w) flow_out[(size_t)gy * g.w + gx] = f;
-                    }
-                } else {
-                    update_matrices_px(slot_plane(b, slot, 0, 0), slot_plane(b, slot, 1, 0), b.plane, Sp, Sw, Sh,
-                                       x, y, f.x, f.y, slot_plane(b, slot, 2, 0));
+    }
+    __syncthreads();
+    float* __restrict__ dst = slot_plane(b, slot, 3, c);  // V^T plane: row = x, column = y, pitch SpT
+    for (int p = threadIdx.x; p < kRowF * OUT; p += 256) {
+        int xx = p / OUT, yy = p % OUT;
+        if (x0 + xx < Sw && y0 + yy < Sh) dst[(size_t)(x0 + xx) * b.SpT + y0 + yy] = stage[xx * SP + yy];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3b: horizontal pass + 2x2 solve + (UpdateMatrices | final scatter).  CTA = 64 rows (y) x 64 columns
+// (x) of one tile, all 5 planes.  The planes of V^T stream through two shared-memory buffers (TMA box
+// = 64 y-values x (64 + 2m) x-rows; plane c+2 is in flight while plane c is convolved); lanes <-> row
+// pairs; the five blurred values of a pixel stay in registers until the f64 solve.  The flow block is
+// then transposed through shared memory so that R0 / R1 / M / flow are accessed with lanes <-> x.
+// grid = (ceil(Sh/64), ceil(Sw/64), ntiles), dynamic smem = 2 * (64 + 2m) * 256 B
+// ------------------------------------------------------------------------------------------------
+constexpr int kFlowPitch = 66;  // float2 per x-row of the flow stage (64 + 2: 16-byte aligned rows, few bank conflicts)
+
+__global__ void __launch_bounds__(256, 1) fb_blur_h_kernel(const __grid_constant__ CUtensorMap mapVT, FbBatch b,
+                                                            const __grid_constant__ FbConsts cst, int last_iter,
+                                                            float2* __restrict__ flow_out) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t bars[2];
+    const TileGeom& g = b.g;
+    const int Sh = g.Sh, Sw = g.Sw, m = cst.m;
+    const int slot = blockIdx.z;
+    const int y0 = blockIdx.x * kRowF, x0 = blockIdx.y * kStep;
+    const int rows = kStep + 2 * m;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* buf[2] = {smem, smem + rows * kRowF};
+    const uint32_t box_bytes = rows * kRowF * sizeof(float);
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int c = 0; c < 2; ++c) {
+            mbar_expect_tx(&bars[c], box_bytes);
+            tma_load_3d(buf[c], &mapVT, y0, x0 - m, slot * 20 + 15 + c, &bars[c]);
+        }
+    }
+    const u64 nz = *reinterpret_cast<const u64*>(&cst.negzero2);
+    u64 acc[5][kR];
+    const bool active = x0 + warp * kR < Sw;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        mbar_wait(&bars[c & 1], (c >> 1) & 1);
+        replicate_edges(buf[c & 1], rows, x0 - m, Sw);
+        if (active) conv8x2(reinterpret_cast<const u64*>(buf[c & 1]) + (warp * kR + m) * kRowU + lane, m, cst.k2, nz, acc[c]);
+        __syncthreads();  // buffer c&1 is free again
+        if (c + 2 < 5 && threadIdx.x == 0) {
+            mbar_expect_tx(&bars[c & 1], box_bytes);
+            tma_load_3d(buf[c & 1], &mapVT, y0, x0 - m, slot * 20 + 15 + c + 2, &bars[c & 1]);
+        }
+    }
+    // 2x2 solve in f64 (FarnebackUpdateFlow_GaussianBlur), flow staged as [x][y]
+    float2* fl = reinterpret_cast<float2*>(smem);  // both input buffers are free now; host sizes smem >= the stage
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < kR; ++j) {
+            float2 G11 = unpack2(acc[0][j]), G12 = unpack2(acc[1][j]), G22 = unpack2(acc[2][j]);
+            float2 H1 = unpack2(acc[3][j]), H2 = unpack2(acc[4][j]);
+            float4 o;
+            {
+                double g11 = G11.x, g12 = G12.x, g22 = G22.x, h1 = H1.x, h2 = H2.x;
+                double idet = __ddiv_rn(1.0, __dadd_rn(__dsub_rn(__dmul_rn(g11, g22), __dmul_rn(g12, g12)), 1e-3));
+                o.x = (float)__dmul_rn(__dsub_rn(__dmul_rn(g11, h2), __dmul_rn(g12, h1)), idet);
+                o.y = (float)__dmul_rn(__dsub_rn(__dmul_rn(g22, h1), __dmul_rn(g12, h2)), idet);
+            }
+            {
+                double g11 = G11.y, g12 = G12.y, g22 = G22.y, h1 = H1.y, h2 = H2.y;
+                double idet = __ddiv_rn(1.0, __dadd_rn(__dsub_rn(__dmul_rn(g11, g22), __dmul_rn(g12, g12)), 1e-3));
+                o.z = (float)__dmul_rn(__dsub_rn(__dmul_rn(g11, h2), __dmul_rn(g12, h1)), idet);
+                o.w = (float)__dmul_rn(__dsub_rn(__dmul_rn(g22, h1), __dmul_rn(g12, h2)), idet);
+            }
+            *reinterpret_cast<float4*>(&fl[(warp * kR + j) * kFlowPitch + 2 * lane]) = o;
+        }
+    }
+    __syncthreads();
+    // epilogue: lanes <-> x
+    const int tile = b.tile0 + slot;
+    const int ti = tile / g.nx, tj = tile % g.nx;
+    const int cx = threadIdx.x & 63, x = x0 + cx;
+    if (x < Sw) {
+        for (int r = threadIdx.x >> 6; r < kRowF; r += 4) {
+            int y = y0 + r;
+            if (y >= Sh) break;
+            float2 f = fl[cx * kFlowPitch + r];
+            if (last_iter) {
+                int cy = y - g.ov, cxx = x - g.ov;
+                if ((unsigned)cy < (unsigned)g.Th && (unsigned)cxx < (unsigned)g.Tw) {
+                    int gy = ti * g.Th + cy, gx = tj * g.Tw + cxx;
+                    if (gy < g.h && gx < g.w) flow_out[(size_t)gy * g.w + gx] = f;
                 }
+            } else {
+                update_matrices_px(slot_plane(b, slot, 0, 0), slot_plane(b, slot, 1, 0), b.plane, b.Sp, Sw, Sh,
+                                   x, y, f.x, f.y, slot_plane(b, slot, 2, 0));
             }
         }
     }
@@ -423,15 +516,19 @@ static void make_consts(int win, FbConsts& c) {
     int m = win / 2;
     c.m = m;
     double sg = m * 0.3, sum = 1;
-    c.k[0] = 1.0f;
+    c.negzero2 = make_float2(-0.0f, -0.0f);
+    float k[kMaxM + 1];
+    k[0] = 1.0f;
     for (int i = 1; i <= m; i++) {
         float t = (float)std::exp(-i * i / (2 * sg * sg));
-        c.k[i] = t;
+        k[i] = t;
         sum += t * 2;
     }
     sum = 1. / sum;
-    for (int i = 0; i <= m; i++) c.k[i] = (float)(c.k[i] * sum);
-    for (int i = m + 1; i <= kMaxM; i++) c.k[i] = 0.0f;
+    for (int i = 0; i <= kMaxM; i++) {
+        float v = i <= m ? (float)(k[i] * sum) : 0.0f;
+        c.k2[i] = make_float2(v, v);
+    }
 }
 
 static inline int plane_pitch(int Sw) { return (Sw + 31) / 32 * 32; }
@@ -440,10 +537,14 @@ static inline int plane_pitch(int Sw) { return (Sw + 31) / 32 * 32; }
 
 using namespace ma;
 
+static inline size_t plane_floats(const TileGeom& g) {
+    return std::max((size_t)g.Sh * plane_pitch(g.Sw), (size_t)g.Sw * plane_pitch(g.Sh));
+}
+
 extern "C" size_t ma_farneback_workspace_bytes(int h, int w, int T, int ov, int n_batch) {
     if (h <= 0 || w <= 0 || n_batch <= 0) return 0;
     TileGeom g = make_geom(h, w, T, ov);
-    return (size_t)n_batch * 20 * (size_t)g.Sh * plane_pitch(g.Sw) * sizeof(float);
+    return (size_t)n_batch * 20 * plane_floats(g) * sizeof(float);
 }
 
 extern "C" int ma_farneback_tiles(const void* mov, const void* ref, size_t pitch, int dtype, int h, int w,
@@ -459,8 +560,9 @@ extern "C" int ma_farneback_tiles(const void* mov, const void* ref, size_t pitch
     int ntot = g.ny * g.nx;
     if (tile_begin < 0 || tile_end > ntot || tile_begin > tile_end) return invalid("ma_farneback_tiles: bad tile range");
     if (tile_begin == tile_end) return MA_OK;
-    int Sp = plane_pitch(g.Sw);
-    size_t plane = (size_t)g.Sh * Sp;
+    int Sp = plane_pitch(g.Sw), SpT = plane_pitch(g.Sh);
+    size_t plane = plane_floats(g);
+    if ((reinterpret_cast<uintptr_t>(workspace) & 127) != 0) return invalid("ma_farneback_tiles: workspace must be 128-byte aligned");
     size_t slot_bytes = 20 * plane * sizeof(float);
     int cap = (int)std::min<size_t>(workspace_bytes / slot_bytes, 4096);
     if (cap < 1) {
@@ -470,34 +572,46 @@ extern "C" int ma_farneback_tiles(const void* mov, const void* ref, size_t pitch
     FbConsts cst;
     make_consts(win, cst);
     cudaStream_t s = (cudaStream_t)stream;
+    const int m = cst.m;
+    const int vout = (m <= 49) ? 128 : 64;  // V-pass rows per CTA: box rows vout + 2m must stay <= 256
+    const size_t v_smem = std::max((size_t)(vout + 2 * m) * kRowF * sizeof(float), (size_t)kRowF * (vout + 1) * sizeof(float));
+    const size_t h_smem = std::max((size_t)2 * (kStep + 2 * m) * kRowF * sizeof(float), (size_t)kStep * kFlowPitch * sizeof(float2));
     static bool attr_set = false;
     if (!attr_set) {
-        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlurHSmem));
+        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 256));
+        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 256));
+        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 256));
         attr_set = true;
     }
     for (int t0 = tile_begin; t0 < tile_end; t0 += cap) {
         FbBatch b;
         b.g = g; b.tile0 = t0; b.ntiles = std::min(cap, tile_end - t0);
-        b.Sp = Sp; b.plane = plane; b.ws = (float*)workspace;
+        b.Sp = Sp; b.SpT = SpT; b.plane = plane; b.ws = (float*)workspace;
         dim3 pg(ceil_div(g.Sw, PE_BW), ceil_div(g.Sh, PE_BH), b.ntiles * 2), pb(PE_BW, PE_BH);
+        double tpx = (double)b.ntiles * g.Sh * g.Sw;
+        { KernelScope ks(K_POLYEXP, s, tpx);
         if (dtype == MA_U8)
             fb_polyexp_kernel<uint8_t><<<pg, pb, 0, s>>>((const uint8_t*)mov, (const uint8_t*)ref, pitch, b, cst);
         else
-            fb_polyexp_kernel<uint16_t><<<pg, pb, 0, s>>>((const uint16_t*)mov, (const uint16_t*)ref, pitch, b, cst);
-        fb_update0_kernel<<<dim3(ceil_div(g.Sw, 64), ceil_div(g.Sh, 4), b.ntiles), 256, 0, s>>>(b);
-        // split strips into segments when the grid would not fill the GPU (each segment re-reads a 2m halo)
-        int vstrips = ceil_div(g.Sw, kLanes) * b.ntiles * 5, hstrips = ceil_div(g.Sh, kLanes) * b.ntiles;
-        int vseg = 1, hseg = 1;
-        while (vstrips * vseg < 148 * 4 && ceil_div(g.Sh, vseg * 2) >= 2 * kStep) vseg *= 2;
-        while (hstrips * hseg < 148 && ceil_div(g.Sw, hseg * 2) >= 2 * kStep) hseg *= 2;
-        int rows_per_seg = ceil_div(ceil_div(g.Sh, vseg), kR) * kR;
-        int cols_per_seg = ceil_div(ceil_div(g.Sw, hseg), kR) * kR;
-        vseg = ceil_div(g.Sh, rows_per_seg);
-        hseg = ceil_div(g.Sw, cols_per_seg);
+            fb_polyexp_kernel<uint16_t><<<pg, pb, 0, s>>>((const uint16_t*)mov, (const uint16_t*)ref, pitch, b, cst); }
+        { KernelScope ks(K_UPDATE0, s, tpx);
+        fb_update0_kernel<<<dim3(ceil_div(g.Sw, 64), ceil_div(g.Sh, 4), b.ntiles), 256, 0, s>>>(b); }
+        // TMA descriptors over this batch's planes: M as [plane][y][x], V^T as [plane][x][y]
+        CUtensorMap mapM, mapVT;
+        uint64_t nplanes = (uint64_t)b.ntiles * 20;
+        if (!make_plane_map(&mapM, b.ws, g.Sw, g.Sh, nplanes, (uint64_t)Sp * 4, plane * 4, kRowF, vout + 2 * m) ||
+            !make_plane_map(&mapVT, b.ws, g.Sh, g.Sw, nplanes, (uint64_t)SpT * 4, plane * 4, kRowF, kStep + 2 * m)) {
+            set_error("ma_farneback_tiles: cuTensorMapEncodeTiled failed");
+            return MA_ERR_CUDA;
+        }
         for (int it = 0; it < iters; ++it) {
-            fb_blur_v_kernel<<<dim3(ceil_div(g.Sw, kLanes), vseg, b.ntiles * 5), 256, 0, s>>>(b, cst, rows_per_seg);
-            fb_blur_h_kernel<<<dim3(ceil_div(g.Sh, kLanes), hseg, b.ntiles), 256, kBlurHSmem, s>>>(
-                b, cst, cols_per_seg, it == iters - 1, (float2*)flow_out);
+            { KernelScope ks(K_BLUR_V, s, tpx);
+            dim3 vg(ceil_div(g.Sw, kRowF), ceil_div(g.Sh, vout), b.ntiles * 5);
+            if (vout == 128) fb_blur_v_kernel<128><<<vg, 256, v_smem, s>>>(mapM, b, cst);
+            else fb_blur_v_kernel<64><<<vg, 256, v_smem, s>>>(mapM, b, cst); }
+            { KernelScope ks(K_BLUR_H, s, tpx);
+            fb_blur_h_kernel<<<dim3(ceil_div(g.Sh, kRowF), ceil_div(g.Sw, kStep), b.ntiles), 256, h_smem, s>>>(
+                mapVT, b, cst, it == iters - 1, (float2*)flow_out); }
         }
         MA_LAUNCH_CHECK("farneback kernels");
     }

@@ -135,8 +135,8 @@ extern "C" int ma_nmi_chunks(const uint8_t* a, const uint8_t* b, size_t n, size_
         int g = (int)std::min<size_t>(kNmiSlots, nchunks - c0);
         MA_CUDA_CHECK(cudaMemsetAsync(hist, 0, (size_t)g * kHistBytes, s));
         int bpc = (int)std::max<size_t>(1, std::min<size_t>((chunk + 256 * 16 - 1) / (256 * 16), (size_t)(148 * 8 + g - 1) / g));
-        nmi_hist_kernel<<<dim3(bpc, g), 256, 0, s>>>(a, b, n, chunk, c0, hist);
-        nmi_entropy_kernel<<<g, 256, 0, s>>>(hist, n, chunk, c0, scores_out);
+        { KernelScope ks(K_NMI_HIST, s, (double)std::min<size_t>(n - c0 * chunk, (size_t)g * chunk)); nmi_hist_kernel<<<dim3(bpc, g), 256, 0, s>>>(a, b, n, chunk, c0, hist); }
+        { KernelScope ks(K_NMI_ENTROPY, s, (double)g); nmi_entropy_kernel<<<g, 256, 0, s>>>(hist, n, chunk, c0, scores_out); }
         MA_LAUNCH_CHECK("nmi kernels");
     }
     return MA_OK;

@@ -79,6 +79,7 @@ extern "C" int ma_pyrdown(const void* src, size_t src_pitch, int h, int w, int d
     int oh = (h + 1) / 2, ow = (w + 1) / 2;
     dim3 block(32, 8), grid(ceil_div(ow, 32), ceil_div(oh, 8));
     cudaStream_t s = (cudaStream_t)stream;
+    KernelScope ks(K_PYRDOWN, s, (double)h * w);
     if (dtype == MA_U8)
         pyrdown_kernel<uint8_t><<<grid, block, 0, s>>>((const uint8_t*)src, src_pitch, h, w, (uint8_t*)dst, dst_pitch, oh, ow);
     else if (dtype == MA_U16)
@@ -95,6 +96,7 @@ extern "C" int ma_pyrup_flow(const float* src, int h, int w, float* dst, int dh,
     if (!((dh == 2 * h || dh == 2 * h - 1) && (dw == 2 * w || dw == 2 * w - 1)) || dh <= 0 || dw <= 0)
         return invalid("ma_pyrup_flow: dstsize must be 2n or 2n-1 per axis");
     dim3 block(32, 8), grid(ceil_div(dw, 32), ceil_div(dh, 8));
+    KernelScope ks(K_PYRUP, (cudaStream_t)stream, (double)dh * dw);
     pyrup_flow_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const float2*)src, h, w, (float2*)dst, dh, dw, scale);
     MA_LAUNCH_CHECK("pyrup_flow_kernel");
     return MA_OK;

@@ -163,6 +163,7 @@ extern "C" int ma_warp_tiles(const void* img, size_t img_pitch, int dtype, const
     TileGeom g = make_geom(h, w, T, ov);
     dim3 block(64, 4), grid(ceil_div(w, 64), ceil_div(h, 4));
     cudaStream_t s = (cudaStream_t)stream;
+    KernelScope ks(K_WARP, s, (double)h * w);
     if (dtype == MA_U8)
         warp_tiles_kernel<uint8_t><<<grid, block, 0, s>>>((const uint8_t*)img, img_pitch, (const float2*)flow, g, (uint8_t*)out, out_pitch);
     else
@@ -186,11 +187,14 @@ extern "C" int ma_merge_flows_tiles(const float* f1, const float* f2, int h, int
     cudaStream_t s = (cudaStream_t)stream;
     int ntiles = g.ny * g.nx;
     unsigned* keys = (unsigned*)workspace;
-    init_keys_kernel<<<ceil_div(2 * ntiles, 256), 256, 0, s>>>(keys, 2 * ntiles);
+    { KernelScope ks(K_SMALL, s);
+    init_keys_kernel<<<ceil_div(2 * ntiles, 256), 256, 0, s>>>(keys, 2 * ntiles); }
     int chunks = max(1, min(64, (int)(((long long)g.Sh * g.Sw) / (256 * 16))));
     if (ntiles > 65535) return invalid("ma_merge_flows_tiles: too many tiles");
-    tile_max_kernel<<<dim3(chunks, ntiles), 256, 0, s>>>((const float2*)f1, (const float2*)f2, g, keys);
+    { KernelScope ks(K_MERGE_MAX, s, (double)h * w);
+    tile_max_kernel<<<dim3(chunks, ntiles), 256, 0, s>>>((const float2*)f1, (const float2*)f2, g, keys); }
     dim3 block(64, 4), grid(ceil_div(w, 64), ceil_div(h, 4));
+    KernelScope ks(K_MERGE, s, (double)h * w);
     merge_tiles_kernel<<<grid, block, 0, s>>>((const float2*)f1, (const float2*)f2, g, keys, (float2*)out);
     MA_LAUNCH_CHECK("merge_tiles_kernel");
     return MA_OK;

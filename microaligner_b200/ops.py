@@ -54,7 +54,20 @@ def to_device(arr, device=None) -> torch.Tensor:
 
 
 def to_host(t: torch.Tensor) -> np.ndarray:
-    return t.cpu().numpy()
+    """Device tensor -> numpy array backed by page-locked memory (torch's caching host allocator
+    recycles the pinned block once the array is garbage collected), one DMA transfer."""
+    host = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return host.numpy()
+
+
+def pinned_like(arr: np.ndarray) -> np.ndarray:
+    """Copy of a numpy array in page-locked host memory (fast H2D for the drop-in numpy API)."""
+    t = torch.empty(arr.shape, dtype=torch.from_numpy(arr[:0]).dtype, pin_memory=True)
+    out = t.numpy()
+    out[...] = arr
+    return out
 
 
 # --------------------------------------------------------------------------------- pyramid

@@ -2,20 +2,7 @@
 import numpy as np
 
 
-def synth_pair(h, w, seed=0, dtype=np.uint16, amp=3.0, period=512.0):
-    """Smooth random texture `ref` and `mov` = ref displaced by a sinusoidal field of amplitude `amp`."""
-    import cv2
-    rng = np.random.default_rng(seed)
-    n = rng.random((h, w), dtype=np.float32)
-    b = cv2.GaussianBlur(n, (0, 0), 3)
-    b = (b - b.min()) / (b.max() - b.min())
-    full = 65535 if dtype == np.uint16 else 255
-    ref = (b * 0.9 * full).astype(dtype)
-    y, x = np.mgrid[0:h, 0:w].astype(np.float32)
-    dx = amp * np.sin(2 * np.pi * y / period)
-    dy = 0.66 * amp * np.cos(2 * np.pi * x / period)
-    mov = cv2.remap(ref, (x + dx).astype(np.float32), (y + dy).astype(np.float32), cv2.INTER_LINEAR)
-    return ref, mov
+from benchdata import synth_pair  # noqa: F401  (re-exported)
 
 
 def blobs(h, w, seed=0, dtype=np.uint16):
