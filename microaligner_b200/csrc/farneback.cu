@@ -4,10 +4,11 @@
 // as called per tile by the reference (optflow_reg/flow_calc.py:30-47, 59-98).
 //
 // Stages (all per S x S tile window; a "tile" is only an index range, never a copy):
-//   fb_polyexp_kernel   u8/u16 window -> 3x3 prefilter (REFLECT_101 at the tile edge) -> polynomial
-//                       expansion n=1 (f32 vertical, f64 horizontal) -> R (5 planar f32 planes)
-//   fb_update0_kernel   M = UpdateMatrices(R0, R1, flow = 0)
-//   fb_blur_v_kernel    V = vertical (2m+1)-tap Gaussian of M, rows replicated at the tile edge
+//   fb_polyexp_kernel   u8/u16 windows of BOTH images -> 3x3 prefilter (REFLECT_101 at the tile edge) ->
+//                       polynomial expansion n=1 (f32 vertical, f64 horizontal) -> R0, R1 (5 planar f32
+//                       planes each) and, fused, M = UpdateMatrices(R0, R1, flow = 0)
+//   fb_blur_v_kernel    V^T = vertical (2m+1)-tap Gaussian of M, rows clamped at the tile edge, stored
+//                       transposed
 //   fb_blur_h_kernel    horizontal (2m+1)-tap Gaussian of V, 2x2 solve in f64 -> flow, then either
 //                       M = UpdateMatrices(R0, R1, flow) in place (not last iteration) or scatter of
 //                       the tile centre into the stitched flow (last iteration).
@@ -16,10 +17,10 @@
 // separately rounded multiply and add.  This file is compiled with -fmad=false and keeps OpenCV's
 // association order (s = c*k0; s += (a[+i] + a[-i]) * k[i], i = 1..m), so results are bit-identical.
 //
-// The two blur kernels are FP32-issue bound (2 passes x 5 planes x (1 + 3m) instr per pixel), not
-// HBM bound; both sweep a strip with a shared-memory ring so each input element is read from
-// global memory exactly once per pass, and every thread keeps 8 outputs + two 8-wide sliding
-// windows in registers so shared-memory traffic is 2 loads per 24 FP instructions.
+// The two blur kernels are FP32-pipe bound (2 passes x 5 planes x (1 + 3m) flops per pixel), not HBM
+// bound.  Inputs arrive by TMA box loads (zero fill outside the plane, edge rows replicated in shared
+// memory afterwards); each thread keeps 8 packed (f32x2) outputs and two 8-deep packed sliding windows
+// in registers, so shared-memory traffic is 2 LDS.64 per 24 packed FP instructions.
 #include <cmath>
 #include <vector>
 #include "common.cuh"
@@ -54,88 +55,164 @@ __device__ __forceinline__ float* slot_plane(const FbBatch& b, int slot, int whi
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1: prefilter + polynomial expansion
+// K1 + K2(first): prefilter + polynomial expansion of BOTH images of a tile, and M0 =
+// UpdateMatrices(R0, R1, flow = 0), fused: with a zero flow the bilinear sample of R1 degenerates
+// to R1 at the same pixel (weights 1,0,0,0), so M0 is a pointwise function of R0 and R1 and the
+// 40 B/px re-read of a separate pass disappears.
+//
+// CTA = 64 x 16 output pixels, 256 threads x 4 pixels.  Per image: raw window (zero outside the
+// image) -> shared memory once, then row prefilter, column prefilter, vertical expansion pass in
+// shared memory (all f32), horizontal pass in f64 registers.  Border rules are evaluated in
+// tile-local coordinates: REFLECT_101 for the 3x3 prefilter, replicate for the expansion.
 // ------------------------------------------------------------------------------------------------
-constexpr int PE_BW = 32, PE_BH = 8;
+constexpr int PE_BW = 64, PE_BH = 16;
+constexpr int PE_RW = PE_BW + 4, PE_RH = PE_BH + 4;   // raw window
+constexpr int PE_PW = PE_BW + 2, PE_PH = PE_BH + 2;   // prefiltered window (1-px halo for the expansion)
 
 template <typename T>
 __device__ __forceinline__ float window_px(const T* __restrict__ img, size_t pitch, const TileGeom& g,
                                            int oy, int ox, int ty, int tx) {
-    int gy = oy + ty, gx = ox + tx;  // (ty,tx) is inside the window; zero padding outside the image
+    int gy = oy + ty, gx = ox + tx;  // zero padding outside the image
     if ((unsigned)gy >= (unsigned)g.h || (unsigned)gx >= (unsigned)g.w) return 0.0f;
     return (float)__ldg((const T*)((const char*)img + (size_t)gy * pitch) + gx);
 }
 
-template <typename T>
-__global__ void __launch_bounds__(PE_BW* PE_BH) fb_polyexp_kernel(const T* __restrict__ mov, const T* __restrict__ ref,
-                                                                   size_t pitch, FbBatch b,
-                                                                   const __grid_constant__ FbConsts cst) {
-    __shared__ float P[PE_BH + 2][PE_BW + 2];
-    __shared__ float T0[PE_BH][PE_BW + 2], T1[PE_BH][PE_BW + 2], T2[PE_BH][PE_BW + 2];
-    const TileGeom& g = b.g;
-    int slot = blockIdx.z >> 1, which = blockIdx.z & 1;  // 0: prev = moving -> R0, 1: next = reference -> R1
-    const T* img = which ? ref : mov;
-    int tile = b.tile0 + slot;
-    int ti = tile / g.nx, tj = tile % g.nx;
-    int oy = ti * g.Th - g.ov, ox = tj * g.Tw - g.ov;
-    int x0 = blockIdx.x * PE_BW, y0 = blockIdx.y * PE_BH;
-    int tid = threadIdx.y * PE_BW + threadIdx.x;
-
-    // prefiltered image at the (clamped = replicated) positions the expansion will read
-    for (int p = tid; p < (PE_BH + 2) * (PE_BW + 2); p += PE_BW * PE_BH) {
-        int r = p / (PE_BW + 2), c = p % (PE_BW + 2);
-        int py = min(max(y0 - 1 + r, 0), g.Sh - 1), px = min(max(x0 - 1 + c, 0), g.Sw - 1);
-        int xl = reflect101(px - 1, g.Sw), xr = reflect101(px + 1, g.Sw);
-        int yu = reflect101(py - 1, g.Sh), yd = reflect101(py + 1, g.Sh);
-        auto rowf = [&](int yy) {
-            float cc = window_px(img, pitch, g, oy, ox, yy, px);
-            float l = window_px(img, pitch, g, oy, ox, yy, xl), rr = window_px(img, pitch, g, oy, ox, yy, xr);
-            return __fadd_rn(__fmul_rn(cc, 0.5f), __fmul_rn(__fadd_rn(l, rr), 0.25f));
-        };
-        float tu = rowf(yu), tc = rowf(py), td = rowf(yd);
-        P[r][c] = __fadd_rn(__fmul_rn(tc, 0.5f), __fmul_rn(__fadd_rn(tu, td), 0.25f));
-    }
-    __syncthreads();
-    // vertical pass of the expansion (f32): rows r (up), r+1 (centre), r+2 (down)
-    for (int p = tid; p < PE_BH * (PE_BW + 2); p += PE_BW * PE_BH) {
-        int r = p / (PE_BW + 2), c = p % (PE_BW + 2);
-        float s0 = P[r][c], sc = P[r + 1][c], s1 = P[r + 2][c];
-        float pp = __fadd_rn(s0, s1);
-        T0[r][c] = __fadd_rn(__fmul_rn(sc, cst.g0), __fmul_rn(cst.g1, pp));
-        T1[r][c] = __fadd_rn(0.0f, __fmul_rn(cst.xg1, __fsub_rn(s1, s0)));
-        T2[r][c] = __fadd_rn(0.0f, __fmul_rn(cst.xxg1, pp));
-    }
-    __syncthreads();
-    int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    if (x >= g.Sw || y >= g.Sh) return;
-    int r = threadIdx.y, c = threadIdx.x + 1;
-    // horizontal pass: float sums/differences, double accumulation (see oracle/farneback_np.py:polyexp)
-    double b1 = (double)__fmul_rn(T0[r][c], cst.g0);
-    double b3 = (double)__fmul_rn(T1[r][c], cst.g0);
-    double b5 = (double)__fmul_rn(T2[r][c], cst.g0);
-    double tg = (double)__fadd_rn(T0[r][c + 1], T0[r][c - 1]);
-    b1 = __dadd_rn(b1, __dmul_rn(tg, (double)cst.g1));
-    double b4 = __dmul_rn(tg, (double)cst.xxg1);
-    double b2 = (double)__fmul_rn(__fsub_rn(T0[r][c + 1], T0[r][c - 1]), cst.xg1);
-    b3 = __dadd_rn(b3, (double)__fmul_rn(__fadd_rn(T1[r][c + 1], T1[r][c - 1]), cst.g1));
-    double b6 = (double)__fmul_rn(__fsub_rn(T1[r][c + 1], T1[r][c - 1]), cst.xg1);
-    b5 = __dadd_rn(b5, (double)__fmul_rn(__fadd_rn(T2[r][c + 1], T2[r][c - 1]), cst.g1));
-    size_t o = (size_t)y * b.Sp + x;
-    slot_plane(b, slot, which, 0)[o] = (float)__dmul_rn(b3, cst.ig11);
-    slot_plane(b, slot, which, 1)[o] = (float)__dmul_rn(b2, cst.ig11);
-    slot_plane(b, slot, which, 2)[o] = (float)__dadd_rn(__dmul_rn(b1, cst.ig03), __dmul_rn(b5, cst.ig33));
-    slot_plane(b, slot, which, 3)[o] = (float)__dadd_rn(__dmul_rn(b1, cst.ig03), __dmul_rn(b4, cst.ig33));
-    slot_plane(b, slot, which, 4)[o] = (float)__dmul_rn(b6, cst.ig55);
-}
-
-// ------------------------------------------------------------------------------------------------
-// K2: UpdateMatrices for one pixel (FarnebackUpdateMatrices, all f32, left-to-right sums)
-// ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float border_w(int d) {
     // {0.14, 0.14, 0.4472, 0.4472, 0.4472}
     return d < 2 ? 0.14f : 0.4472f;
 }
 
+// second half of FarnebackUpdateMatrices: from the sampled / averaged r2..r6 to the five M entries
+__device__ __forceinline__ void finish_matrices(float q0, float q1, float r2, float r3, float r4, float r5, float r6,
+                                                float dx, float dy, int x, int y, int Sw, int Sh,
+                                                float* __restrict__ M, size_t plane, size_t o) {
+    r2 = __fmul_rn(__fsub_rn(q0, r2), 0.5f);
+    r3 = __fmul_rn(__fsub_rn(q1, r3), 0.5f);
+    r2 = __fadd_rn(r2, __fadd_rn(__fmul_rn(r4, dy), __fmul_rn(r6, dx)));
+    r3 = __fadd_rn(r3, __fadd_rn(__fmul_rn(r6, dy), __fmul_rn(r5, dx)));
+    if ((unsigned)(x - 5) >= (unsigned)(Sw - 10) || (unsigned)(y - 5) >= (unsigned)(Sh - 10)) {
+        float scale = (x < 5 ? border_w(x) : 1.0f);
+        scale = __fmul_rn(scale, (x >= Sw - 5 ? border_w(Sw - x - 1) : 1.0f));
+        scale = __fmul_rn(scale, (y < 5 ? border_w(y) : 1.0f));
+        scale = __fmul_rn(scale, (y >= Sh - 5 ? border_w(Sh - y - 1) : 1.0f));
+        r2 = __fmul_rn(r2, scale); r3 = __fmul_rn(r3, scale); r4 = __fmul_rn(r4, scale);
+        r5 = __fmul_rn(r5, scale); r6 = __fmul_rn(r6, scale);
+    }
+    M[o] = __fadd_rn(__fmul_rn(r4, r4), __fmul_rn(r6, r6));
+    M[plane + o] = __fmul_rn(__fadd_rn(r4, r5), r6);
+    M[2 * plane + o] = __fadd_rn(__fmul_rn(r5, r5), __fmul_rn(r6, r6));
+    M[3 * plane + o] = __fadd_rn(__fmul_rn(r4, r2), __fmul_rn(r6, r3));
+    M[4 * plane + o] = __fadd_rn(__fmul_rn(r6, r2), __fmul_rn(r5, r3));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) fb_polyexp_kernel(const T* __restrict__ mov, const T* __restrict__ ref,
+                                                         size_t pitch, FbBatch b, const __grid_constant__ FbConsts cst) {
+    __shared__ float raw[PE_RH][PE_RW];
+    __shared__ float th[PE_RH][PE_PW];                 // row-prefiltered
+    __shared__ float P[PE_PH][PE_PW];                  // prefiltered image at replicated positions
+    __shared__ float T0[PE_BH][PE_PW], T1[PE_BH][PE_PW], T2[PE_BH][PE_PW];
+    const TileGeom& g = b.g;
+    const int Sh = g.Sh, Sw = g.Sw;
+    const int slot = blockIdx.z;
+    const int tile = b.tile0 + slot;
+    const int ti = tile / g.nx, tj = tile % g.nx;
+    const int oy = ti * g.Th - g.ov, ox = tj * g.Tw - g.ov;
+    const int x0 = blockIdx.x * PE_BW, y0 = blockIdx.y * PE_BH;
+    const int tid = threadIdx.x;
+    const int tx = tid & 63, ty = tid >> 6;
+    float R0v[4][5];
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {          // 0: prev = moving -> R0, 1: next = reference -> R1
+        const T* img = which ? ref : mov;
+        __syncthreads();
+        for (int p = tid; p < PE_RH * PE_RW; p += 256) {
+            int r = p / PE_RW, c = p % PE_RW;
+            int yy = y0 - 2 + r, xx = x0 - 2 + c;
+            float v = 0.0f;
+            if ((unsigned)yy < (unsigned)Sh && (unsigned)xx < (unsigned)Sw) v = window_px(img, pitch, g, oy, ox, yy, xx);
+            raw[r][c] = v;
+        }
+        __syncthreads();
+        for (int p = tid; p < PE_RH * PE_PW; p += 256) {      // rows: actual, columns: replicated positions
+            int r = p / PE_PW, cu = p % PE_PW;
+            int px = min(max(x0 - 1 + cu, 0), Sw - 1);
+            int xl = reflect101(px - 1, Sw), xr = reflect101(px + 1, Sw);
+            const float* row = raw[r] - (x0 - 2);
+            th[r][cu] = __fadd_rn(__fmul_rn(row[px], 0.5f), __fmul_rn(__fadd_rn(row[xl], row[xr]), 0.25f));
+        }
+        __syncthreads();
+        for (int p = tid; p < PE_PH * PE_PW; p += 256) {
+            int rv = p / PE_PW, cu = p % PE_PW;
+            int py = min(max(y0 - 1 + rv, 0), Sh - 1);
+            int yu = reflect101(py - 1, Sh), yd = reflect101(py + 1, Sh);
+            const int ro = y0 - 2;
+            P[rv][cu] = __fadd_rn(__fmul_rn(th[py - ro][cu], 0.5f), __fmul_rn(__fadd_rn(th[yu - ro][cu], th[yd - ro][cu]), 0.25f));
+        }
+        __syncthreads();
+        for (int p = tid; p < PE_BH * PE_PW; p += 256) {      // vertical pass of the expansion (f32)
+            int r = p / PE_PW, c = p % PE_PW;
+            float s0 = P[r][c], sc = P[r + 1][c], s1 = P[r + 2][c];
+            float pp = __fadd_rn(s0, s1);
+            T0[r][c] = __fadd_rn(__fmul_rn(sc, cst.g0), __fmul_rn(cst.g1, pp));
+            T1[r][c] = __fadd_rn(0.0f, __fmul_rn(cst.xg1, __fsub_rn(s1, s0)));
+            T2[r][c] = __fadd_rn(0.0f, __fmul_rn(cst.xxg1, pp));
+        }
+        __syncthreads();
+        const int x = x0 + tx;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int r = ty + 4 * q, y = y0 + r, c = tx + 1;
+            if (x >= Sw || y >= Sh) continue;
+            // horizontal pass: float sums/differences, double accumulation (oracle/farneback_np.py:polyexp)
+            double b1 = (double)__fmul_rn(T0[r][c], cst.g0);
+            double b3 = (double)__fmul_rn(T1[r][c], cst.g0);
+            double b5 = (double)__fmul_rn(T2[r][c], cst.g0);
+            double tg = (double)__fadd_rn(T0[r][c + 1], T0[r][c - 1]);
+            b1 = __dadd_rn(b1, __dmul_rn(tg, (double)cst.g1));
+            double b4 = __dmul_rn(tg, (double)cst.xxg1);
+            double b2 = (double)__fmul_rn(__fsub_rn(T0[r][c + 1], T0[r][c - 1]), cst.xg1);
+            b3 = __dadd_rn(b3, (double)__fmul_rn(__fadd_rn(T1[r][c + 1], T1[r][c - 1]), cst.g1));
+            double b6 = (double)__fmul_rn(__fsub_rn(T1[r][c + 1], T1[r][c - 1]), cst.xg1);
+            b5 = __dadd_rn(b5, (double)__fmul_rn(__fadd_rn(T2[r][c + 1], T2[r][c - 1]), cst.g1));
+            float v[5];
+            v[0] = (float)__dmul_rn(b3, cst.ig11);
+            v[1] = (float)__dmul_rn(b2, cst.ig11);
+            v[2] = (float)__dadd_rn(__dmul_rn(b1, cst.ig03), __dmul_rn(b5, cst.ig33));
+            v[3] = (float)__dadd_rn(__dmul_rn(b1, cst.ig03), __dmul_rn(b4, cst.ig33));
+            v[4] = (float)__dmul_rn(b6, cst.ig55);
+            const size_t o = (size_t)y * b.Sp + x;
+            float* Rp = slot_plane(b, slot, which, 0);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) Rp[k * b.plane + o] = v[k];
+            if (which == 0) {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) R0v[q][k] = v[k];
+            } else {
+                // UpdateMatrices with flow == 0: sample of R1 = R1 itself where (x, y) has a right/lower neighbour
+                float r2, r3, r4, r5, r6;
+                if (x < Sw - 1 && y < Sh - 1) {
+                    r2 = v[0];
+                    r3 = v[1];
+                    r4 = __fmul_rn(__fadd_rn(R0v[q][2], v[2]), 0.5f);
+                    r5 = __fmul_rn(__fadd_rn(R0v[q][3], v[3]), 0.5f);
+                    r6 = __fmul_rn(__fadd_rn(R0v[q][4], v[4]), 0.25f);
+                } else {
+                    r2 = r3 = 0.0f;
+                    r4 = R0v[q][2];
+                    r5 = R0v[q][3];
+                    r6 = __fmul_rn(R0v[q][4], 0.5f);
+                }
+                finish_matrices(R0v[q][0], R0v[q][1], r2, r3, r4, r5, r6, 0.0f, 0.0f, x, y, Sw, Sh,
+                                slot_plane(b, slot, 2, 0), b.plane, o);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: UpdateMatrices for one pixel (FarnebackUpdateMatrices, all f32, left-to-right sums)
+// ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void update_matrices_px(const float* __restrict__ R0, const float* __restrict__ R1,
                                                    size_t plane, int Sp, int Sw, int Sh, int x, int y,
                                                    float dx, float dy, float* __restrict__ M) {
@@ -169,32 +246,7 @@ __device__ __forceinline__ void update_matrices_px(const float* __restrict__ R0,
         r5 = q3;
         r6 = __fmul_rn(q4, 0.5f);
     }
-    r2 = __fmul_rn(__fsub_rn(__ldg(R0 + o), r2), 0.5f);
-    r3 = __fmul_rn(__fsub_rn(__ldg(R0 + plane + o), r3), 0.5f);
-    r2 = __fadd_rn(r2, __fadd_rn(__fmul_rn(r4, dy), __fmul_rn(r6, dx)));
-    r3 = __fadd_rn(r3, __fadd_rn(__fmul_rn(r6, dy), __fmul_rn(r5, dx)));
-    if ((unsigned)(x - 5) >= (unsigned)(Sw - 10) || (unsigned)(y - 5) >= (unsigned)(Sh - 10)) {
-        float scale = (x < 5 ? border_w(x) : 1.0f);
-        scale = __fmul_rn(scale, (x >= Sw - 5 ? border_w(Sw - x - 1) : 1.0f));
-        scale = __fmul_rn(scale, (y < 5 ? border_w(y) : 1.0f));
-        scale = __fmul_rn(scale, (y >= Sh - 5 ? border_w(Sh - y - 1) : 1.0f));
-        r2 = __fmul_rn(r2, scale); r3 = __fmul_rn(r3, scale); r4 = __fmul_rn(r4, scale);
-        r5 = __fmul_rn(r5, scale); r6 = __fmul_rn(r6, scale);
-    }
-    M[o] = __fadd_rn(__fmul_rn(r4, r4), __fmul_rn(r6, r6));
-    M[plane + o] = __fmul_rn(__fadd_rn(r4, r5), r6);
-    M[2 * plane + o] = __fadd_rn(__fmul_rn(r5, r5), __fmul_rn(r6, r6));
-    M[3 * plane + o] = __fadd_rn(__fmul_rn(r4, r2), __fmul_rn(r6, r3));
-    M[4 * plane + o] = __fadd_rn(__fmul_rn(r6, r2), __fmul_rn(r5, r3));
-}
-
-__global__ void __launch_bounds__(256) fb_update0_kernel(FbBatch b) {
-    int x = blockIdx.x * 64 + (threadIdx.x & 63);
-    int y = blockIdx.y * 4 + (threadIdx.x >> 6);
-    int slot = blockIdx.z;
-    if (x >= b.g.Sw || y >= b.g.Sh) return;
-    update_matrices_px(slot_plane(b, slot, 0, 0), slot_plane(b, slot, 1, 0), b.plane, b.Sp, b.g.Sw, b.g.Sh,
-                       x, y, 0.0f, 0.0f, slot_plane(b, slot, 2, 0));
+    finish_matrices(__ldg(R0 + o), __ldg(R0 + plane + o), r2, r3, r4, r5, r6, dx, dy, x, y, Sw, Sh, M, plane, o);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -360,7 +412,7 @@ __global__ void __launch_bounds__(256) fb_blur_v_kernel(const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------
 constexpr int kFlowPitch = 66;  // float2 per x-row of the flow stage (64 + 2: 16-byte aligned rows, few bank conflicts)
 
-__global__ void __launch_bounds__(256, 1) fb_blur_h_kernel(const __grid_constant__ CUtensorMap mapVT, FbBatch b,
+__global__ void __launch_bounds__(256, 2) fb_blur_h_kernel(const __grid_constant__ CUtensorMap mapVT, FbBatch b,
                                                             const __grid_constant__ FbConsts cst, int last_iter,
                                                             float2* __restrict__ flow_out) {
     extern __shared__ __align__(128) float smem[];
@@ -587,15 +639,13 @@ extern "C" int ma_farneback_tiles(const void* mov, const void* ref, size_t pitch
         FbBatch b;
         b.g = g; b.tile0 = t0; b.ntiles = std::min(cap, tile_end - t0);
         b.Sp = Sp; b.SpT = SpT; b.plane = plane; b.ws = (float*)workspace;
-        dim3 pg(ceil_div(g.Sw, PE_BW), ceil_div(g.Sh, PE_BH), b.ntiles * 2), pb(PE_BW, PE_BH);
         double tpx = (double)b.ntiles * g.Sh * g.Sw;
         { KernelScope ks(K_POLYEXP, s, tpx);
+        dim3 pg(ceil_div(g.Sw, PE_BW), ceil_div(g.Sh, PE_BH), b.ntiles);
         if (dtype == MA_U8)
-            fb_polyexp_kernel<uint8_t><<<pg, pb, 0, s>>>((const uint8_t*)mov, (const uint8_t*)ref, pitch, b, cst);
+            fb_polyexp_kernel<uint8_t><<<pg, 256, 0, s>>>((const uint8_t*)mov, (const uint8_t*)ref, pitch, b, cst);
         else
-            fb_polyexp_kernel<uint16_t><<<pg, pb, 0, s>>>((const uint16_t*)mov, (const uint16_t*)ref, pitch, b, cst); }
-        { KernelScope ks(K_UPDATE0, s, tpx);
-        fb_update0_kernel<<<dim3(ceil_div(g.Sw, 64), ceil_div(g.Sh, 4), b.ntiles), 256, 0, s>>>(b); }
+            fb_polyexp_kernel<uint16_t><<<pg, 256, 0, s>>>((const uint16_t*)mov, (const uint16_t*)ref, pitch, b, cst); }
         // TMA descriptors over this batch's planes: M as [plane][y][x], V^T as [plane][x][y]
         CUtensorMap mapM, mapVT;
         uint64_t nplanes = (uint64_t)b.ntiles * 20;
