@@ -50,10 +50,18 @@ int ma_pyrdown(const void* src, size_t src_pitch, int h, int w, int dtype,
  * pre-multiplication of the flow (1, 2 or 4). */
 int ma_pyrup_flow(const float* src, int h, int w, float* dst, int dh, int dw, float scale, void* stream);
 
+/* same, restricted to destination rows [row_begin, row_end) */
+int ma_pyrup_flow_rows(const float* src, int h, int w, float* dst, int dh, int dw, float scale,
+                       int row_begin, int row_end, void* stream);
+
 /* ---- Warper.warp (optflow_reg/warper.py:37-76): per-tile cv.remap(INTER_LINEAR, constant 0) of
  * `img` by map = tile-local grid - flow, tile centres written to `out`. dtype MA_U8|MA_U16. */
 int ma_warp_tiles(const void* img, size_t img_pitch, int dtype, const float* flow, int h, int w,
                   int T, int ov, void* out, size_t out_pitch, void* stream);
+
+/* same, restricted to output rows [row_begin, row_end) (multi-GPU row bands) */
+int ma_warp_tiles_rows(const void* img, size_t img_pitch, int dtype, const float* flow, int h, int w,
+                       int T, int ov, void* out, size_t out_pitch, int row_begin, int row_end, void* stream);
 
 /* ---- merge_two_flows per tile + stitch (optflow_reg/optflow_registrator.py:37-47, 217-240):
  * per tile: max(f1)==0 -> f2; max(f2)==0 -> f1; else f1 + remap(f2, map = -f1).
@@ -61,6 +69,10 @@ int ma_warp_tiles(const void* img, size_t img_pitch, int dtype, const float* flo
 size_t ma_merge_workspace_bytes(int h, int w, int T);
 int ma_merge_flows_tiles(const float* f1, const float* f2, int h, int w, int T, int ov,
                          float* out, void* workspace, void* stream);
+
+/* same, restricted to the tiles of tile rows [tile_row_begin, tile_row_end) */
+int ma_merge_flows_tile_rows(const float* f1, const float* f2, int h, int w, int T, int ov, float* out,
+                             void* workspace, int tile_row_begin, int tile_row_end, void* stream);
 
 /* ---- tiled Farneback: TileFlowCalc.calc_flow / farneback (optflow_reg/flow_calc.py:30-98) =
  * cv.calcOpticalFlowFarneback(mov, ref, None, 0.5, 0, win, iters, 1, 1.7, FARNEBACK_GAUSSIAN)
@@ -82,6 +94,16 @@ size_t ma_dog_workspace_bytes(int h, int w);
 int ma_dog_u8(const void* src, size_t src_pitch, int dtype, int h, int w,
               uint8_t* dst, size_t dst_pitch, void* workspace, void* stream);
 
+/* The two phases of ma_dog_u8 on a band of rows, for row-sharded execution: the caller supplies the
+ * GLOBAL min/max of the source (device float[2]) and later of the difference image (after reducing the
+ * per-band values ma_dog_diff_rows returns in diff_minmax).  diff is an (h, ma_dog_diff_pitch_floats(w))
+ * float plane; source rows [row_begin-20, row_end+20) must be valid. */
+size_t ma_dog_diff_pitch_floats(int w);
+int ma_dog_diff_rows(const void* src, size_t src_pitch, int dtype, int h, int w, const float* src_minmax,
+                     int row_begin, int row_end, float* diff, float* diff_minmax, void* workspace, void* stream);
+int ma_dog_quantize_rows(const float* diff, int h, int w, const float* diff_minmax, int row_begin, int row_end,
+                         uint8_t* dst, size_t dst_pitch, void* stream);
+
 /* ---- mi_tiled (shared_modules/similarity_scoring.py:27-50): normalized mutual information
  * (sklearn, arithmetic mean, natural log) of two u8 label images over consecutive chunks of
  * `chunk` row-major elements of the dense n-element arrays; scores_out[c] (double, device) gets
@@ -89,6 +111,10 @@ int ma_dog_u8(const void* src, size_t src_pitch, int dtype, int h, int w,
 size_t ma_nmi_workspace_bytes(size_t n, size_t chunk);
 int ma_nmi_chunks(const uint8_t* a, const uint8_t* b, size_t n, size_t chunk,
                   double* scores_out, void* workspace, void* stream);
+
+/* same for chunks [chunk_begin, chunk_end) only (other entries of scores_out are left untouched) */
+int ma_nmi_chunk_range(const uint8_t* a, const uint8_t* b, size_t n, size_t chunk, size_t chunk_begin, size_t chunk_end,
+                       double* scores_out, void* workspace, void* stream);
 
 /* ---- pipeline input prep (shared_modules/utils.py:75-95): z max-projection of n_pages images
  * followed by cv.normalize(.., 0, 255, NORM_MINMAX, CV_8U). pages_host is a HOST array of n_pages

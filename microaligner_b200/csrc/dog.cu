@@ -89,15 +89,15 @@ __global__ void keys_to_float_kernel(const unsigned* keys, float* out2) {
 }
 
 // scale/shift of cv.normalize(.., 0, 1, NORM_MINMAX, CV_32F)
-__device__ __forceinline__ void norm01_coeffs(const unsigned* keys, float& a, float& b) {
-    double smin = key2f(keys[0]), smax = key2f(keys[1]);
+__device__ __forceinline__ void norm01_coeffs(const float* __restrict__ mm, float& a, float& b) {
+    double smin = mm[0], smax = mm[1];
     double scale = (smax - smin > 2.220446049250313e-16) ? __ddiv_rn(1.0, __dsub_rn(smax, smin)) : 0.0;
     a = (float)scale;
     b = __fsub_rn(0.0f, (float)__dmul_rn(smin, (double)a));
 }
 // scale/shift of cv.normalize(.., 0, 255, NORM_MINMAX, CV_8U)
-__device__ __forceinline__ void norm255_coeffs(const unsigned* keys, float& a, float& b) {
-    double smin = key2f(keys[0]), smax = key2f(keys[1]);
+__device__ __forceinline__ void norm255_coeffs(const float* __restrict__ mm, float& a, float& b) {
+    double smin = mm[0], smax = mm[1];
     double scale = __dmul_rn(255.0, (smax - smin > 2.220446049250313e-16) ? __ddiv_rn(1.0, __dsub_rn(smax, smin)) : 0.0);
     double shift = __dsub_rn(0.0, __dmul_rn(smin, scale));
     a = (float)scale;
@@ -113,14 +113,15 @@ constexpr int DOG_HROWS = 2;           // rows per block
 
 template <typename T>
 __global__ void __launch_bounds__(DOG_HT* DOG_HROWS) dog_row_kernel(const T* __restrict__ src, size_t pitch, int h, int w,
-                                                                     const unsigned* __restrict__ keys,
+                                                                     const float* __restrict__ src_mm,
                                                                      float* __restrict__ A5, float* __restrict__ A9, int wp,
-                                                                     const __grid_constant__ DogTaps taps) {
+                                                                     const __grid_constant__ DogTaps taps, int ybeg, int yend) {
     __shared__ __align__(16) float seg[DOG_HROWS][DOG_HW + 40];
-    int ry = threadIdx.y, y = blockIdx.y * DOG_HROWS + ry;
+    int ry = threadIdx.y, y = ybeg + blockIdx.y * DOG_HROWS + ry;
     int xb = blockIdx.x * DOG_HW;
     float a, b;
-    norm01_coeffs(keys, a, b);
+    norm01_coeffs(src_mm, a, b);
+    h = yend;  // rows [ybeg, yend) of the image are filtered
     if (y < h) {
         const T* row = (const T*)((const char*)src + (size_t)y * pitch);
         for (int i = threadIdx.x; i < DOG_HW + 40; i += DOG_HT) {
@@ -189,12 +190,12 @@ __device__ __forceinline__ void col_conv8(const float* __restrict__ P, int wp, i
 
 __global__ void __launch_bounds__(256) dog_col_kernel(const float* __restrict__ A5, const float* __restrict__ A9, int wp, int h, int w,
                                                       float* __restrict__ D, unsigned* keys_out,
-                                                      const __grid_constant__ DogTaps taps) {
+                                                      const __grid_constant__ DogTaps taps, int ybeg, int yend) {
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int x = blockIdx.x * 32 + lane;
-    int y0 = (blockIdx.y * 8 + warp) * DOG_VR;
+    int y0 = ybeg + (blockIdx.y * 8 + warp) * DOG_VR;
     float lo = INFINITY, hi = -INFINITY;
-    if (x < w && y0 < h) {
+    if (x < w && y0 < yend) {
         float s5[DOG_VR], s9[DOG_VR];
         if (x < (w & ~7)) {
             col_conv8<true>(A5, wp, h, x, y0, taps.k5, s5);
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(256) dog_col_kernel(const float* __restrict__ 
         }
 #pragma unroll
         for (int o = 0; o < DOG_VR; ++o) {
-            if (y0 + o < h) {
+            if (y0 + o < yend) {
                 float d = __fsub_rn(s9[o], s5[o]);
                 D[(size_t)(y0 + o) * wp + x] = d;
                 lo = fminf(lo, d);
@@ -217,10 +218,10 @@ __global__ void __launch_bounds__(256) dog_col_kernel(const float* __restrict__ 
 }
 
 __global__ void __launch_bounds__(256) dog_quant_kernel(const float* __restrict__ D, int wp, int h, int w,
-                                                        const unsigned* __restrict__ keys, uint8_t* __restrict__ dst, size_t dp) {
+                                                        const float* __restrict__ mm, uint8_t* __restrict__ dst, size_t dp, int ybeg) {
     float a, b;
-    norm255_coeffs(keys, a, b);
-    int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+    norm255_coeffs(mm, a, b);
+    int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = ybeg + blockIdx.y;
     if (x >= w) return;
     const float* row = D + (size_t)y * wp;
     uint8_t* out = dst + (size_t)y * dp;
@@ -265,7 +266,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) norm_u8_kernel(const T* __restrict__ mip, int mp, int h, int w, const unsigned* __restrict__ keys,
                                                       uint8_t* __restrict__ dst, size_t dp) {
     float a, b;
-    norm255_coeffs(keys, a, b);
+    float mm[2] = {key2f(keys[0]), key2f(keys[1])};
+    norm255_coeffs(mm, a, b);
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= w) return;
     float v = (float)mip[(size_t)y * mp + x];
@@ -300,35 +302,63 @@ extern "C" size_t ma_dog_workspace_bytes(int h, int w) {
     return 256 + 3 * (size_t)h * pad4(w) * sizeof(float);
 }
 
+extern "C" size_t ma_dog_diff_pitch_floats(int w) { return (size_t)pad4(w); }
+
+// phase 1: rows [row_begin, row_end) of d = blur9(f) - blur5(f), f = normalised src, plus min/max of those rows
+extern "C" int ma_dog_diff_rows(const void* src, size_t src_pitch, int dtype, int h, int w, const float* src_minmax,
+                                int row_begin, int row_end, float* diff, float* diff_minmax, void* workspace, void* stream) {
+    if (!src || !src_minmax || !diff || !diff_minmax || !workspace) return invalid("ma_dog_diff_rows: null pointer");
+    if (h < 21 || w < 21) return invalid("ma_dog_u8: image must be at least 21 x 21 (single-reflection border)");
+    if (dtype != MA_U8 && dtype != MA_U16) return invalid("ma_dog_u8: dtype must be MA_U8 or MA_U16");
+    if (row_begin < 0 || row_end > h || row_begin > row_end) return invalid("ma_dog_diff_rows: bad row range");
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned* keys = (unsigned*)workspace;
+    int wp = pad4(w);
+    float* A5 = (float*)((char*)workspace + 256);
+    float* A9 = A5 + (size_t)h * wp;
+    static DogTaps taps;
+    static bool taps_ready = false;
+    if (!taps_ready) { make_dog_taps(taps); taps_ready = true; }
+    { KernelScope ks(K_SMALL, s); init_minmax_keys<<<1, 32, 0, s>>>(keys, 1); }
+    if (row_begin < row_end) {
+        int ra = std::max(row_begin - 20, 0), rb = std::min(row_end + 20, h);
+        double px = (double)(row_end - row_begin) * w;
+        dim3 rg(ceil_div(w, DOG_HW), ceil_div(rb - ra, DOG_HROWS)), rbk(DOG_HT, DOG_HROWS);
+        { KernelScope ks(K_DOG_ROW, s, px);
+        if (dtype == MA_U8) dog_row_kernel<uint8_t><<<rg, rbk, 0, s>>>((const uint8_t*)src, src_pitch, h, w, src_minmax, A5, A9, wp, taps, ra, rb);
+        else dog_row_kernel<uint16_t><<<rg, rbk, 0, s>>>((const uint16_t*)src, src_pitch, h, w, src_minmax, A5, A9, wp, taps, ra, rb); }
+        { KernelScope ks(K_DOG_COL, s, px);
+        dog_col_kernel<<<dim3(ceil_div(w, 32), ceil_div(row_end - row_begin, 8 * DOG_VR)), 256, 0, s>>>(A5, A9, wp, h, w, diff, keys, taps, row_begin, row_end); }
+    }
+    { KernelScope ks(K_SMALL, s); keys_to_float_kernel<<<1, 1, 0, s>>>(keys, diff_minmax); }
+    MA_LAUNCH_CHECK("dog diff kernels");
+    return MA_OK;
+}
+
+// phase 2: rows [row_begin, row_end) of the u8 result from d and the GLOBAL min/max of d
+extern "C" int ma_dog_quantize_rows(const float* diff, int h, int w, const float* diff_minmax, int row_begin, int row_end,
+                                    uint8_t* dst, size_t dst_pitch, void* stream) {
+    if (!diff || !diff_minmax || !dst) return invalid("ma_dog_quantize_rows: null pointer");
+    if (row_begin < 0 || row_end > h || row_begin > row_end) return invalid("ma_dog_quantize_rows: bad row range");
+    if (row_begin == row_end) return MA_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    KernelScope ks(K_DOG_QUANT, s, (double)(row_end - row_begin) * w);
+    dog_quant_kernel<<<dim3(ceil_div(ceil_div(w, 4), 256), row_end - row_begin), 256, 0, s>>>(diff, pad4(w), h, w, diff_minmax, dst, dst_pitch, row_begin);
+    MA_LAUNCH_CHECK("dog_quant_kernel");
+    return MA_OK;
+}
+
 extern "C" int ma_dog_u8(const void* src, size_t src_pitch, int dtype, int h, int w,
                          uint8_t* dst, size_t dst_pitch, void* workspace, void* stream) {
     if (!src || !dst || !workspace) return invalid("ma_dog_u8: null pointer");
     if (h < 21 || w < 21) return invalid("ma_dog_u8: image must be at least 21 x 21 (single-reflection border)");
-    if (dtype != MA_U8 && dtype != MA_U16) return invalid("ma_dog_u8: dtype must be MA_U8 or MA_U16");
-    cudaStream_t s = (cudaStream_t)stream;
-    unsigned* keys = (unsigned*)workspace;  // [0,1] src min/max, [2,3] diff min/max
-    int wp = pad4(w);
-    float* A5 = (float*)((char*)workspace + 256);
-    float* A9 = A5 + (size_t)h * wp;
-    float* D = A9 + (size_t)h * wp;
-    static DogTaps taps;
-    static bool taps_ready = false;
-    if (!taps_ready) { make_dog_taps(taps); taps_ready = true; }
-    double px = (double)h * w;
-    { KernelScope ks(K_SMALL, s); init_minmax_keys<<<1, 32, 0, s>>>(keys, 2); }
-    dim3 mg(std::min(ceil_div(w, 256), 8), std::min(h, 1184));
-    dim3 rg(ceil_div(w, DOG_HW), ceil_div(h, DOG_HROWS)), rb(DOG_HT, DOG_HROWS);
-    if (dtype == MA_U8) {
-        { KernelScope ks(K_MINMAX, s, px); minmax_kernel<uint8_t><<<mg, 256, 0, s>>>((const uint8_t*)src, src_pitch, h, w, keys); }
-        { KernelScope ks(K_DOG_ROW, s, px); dog_row_kernel<uint8_t><<<rg, rb, 0, s>>>((const uint8_t*)src, src_pitch, h, w, keys, A5, A9, wp, taps); }
-    } else {
-        { KernelScope ks(K_MINMAX, s, px); minmax_kernel<uint16_t><<<mg, 256, 0, s>>>((const uint16_t*)src, src_pitch, h, w, keys); }
-        { KernelScope ks(K_DOG_ROW, s, px); dog_row_kernel<uint16_t><<<rg, rb, 0, s>>>((const uint16_t*)src, src_pitch, h, w, keys, A5, A9, wp, taps); }
-    }
-    { KernelScope ks(K_DOG_COL, s, px); dog_col_kernel<<<dim3(ceil_div(w, 32), ceil_div(h, 8 * DOG_VR)), 256, 0, s>>>(A5, A9, wp, h, w, D, keys + 2, taps); }
-    { KernelScope ks(K_DOG_QUANT, s, px); dog_quant_kernel<<<dim3(ceil_div(ceil_div(w, 4), 256), h), 256, 0, s>>>(D, wp, h, w, keys + 2, dst, dst_pitch); }
-    MA_LAUNCH_CHECK("dog kernels");
-    return MA_OK;
+    float* mm = (float*)((char*)workspace + 64);       // [0,1] source min/max, [2,3] diff min/max
+    float* D = (float*)((char*)workspace + 256) + 2 * (size_t)h * pad4(w);
+    int rc = ma_minmax(src, src_pitch, dtype, h, w, mm, stream);
+    if (rc) return rc;
+    rc = ma_dog_diff_rows(src, src_pitch, dtype, h, w, mm, 0, h, D, mm + 2, workspace, stream);
+    if (rc) return rc;
+    return ma_dog_quantize_rows(D, h, w, mm + 2, 0, h, dst, dst_pitch, stream);
 }
 
 extern "C" size_t ma_zmip_workspace_bytes(int h, int w, int dtype) {

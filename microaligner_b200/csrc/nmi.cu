@@ -124,15 +124,16 @@ extern "C" size_t ma_nmi_workspace_bytes(size_t n, size_t chunk) {
     return std::min<size_t>(nchunks, kNmiSlots) * kHistBytes;
 }
 
-extern "C" int ma_nmi_chunks(const uint8_t* a, const uint8_t* b, size_t n, size_t chunk,
-                             double* scores_out, void* workspace, void* stream) {
+extern "C" int ma_nmi_chunk_range(const uint8_t* a, const uint8_t* b, size_t n, size_t chunk, size_t chunk_begin, size_t chunk_end,
+                                  double* scores_out, void* workspace, void* stream) {
     if (!a || !b || !scores_out || !workspace || n == 0 || chunk == 0) return invalid("ma_nmi_chunks: bad argument");
     if (chunk > 0xffffffffull) return invalid("ma_nmi_chunks: chunk must fit 32-bit counters");
     cudaStream_t s = (cudaStream_t)stream;
     size_t nchunks = (n + chunk - 1) / chunk;
+    if (chunk_begin > chunk_end || chunk_end > nchunks) return invalid("ma_nmi_chunks: bad chunk range");
     unsigned* hist = (unsigned*)workspace;
-    for (size_t c0 = 0; c0 < nchunks; c0 += kNmiSlots) {
-        int g = (int)std::min<size_t>(kNmiSlots, nchunks - c0);
+    for (size_t c0 = chunk_begin; c0 < chunk_end; c0 += kNmiSlots) {
+        int g = (int)std::min<size_t>(kNmiSlots, chunk_end - c0);
         MA_CUDA_CHECK(cudaMemsetAsync(hist, 0, (size_t)g * kHistBytes, s));
         int bpc = (int)std::max<size_t>(1, std::min<size_t>((chunk + 256 * 16 - 1) / (256 * 16), (size_t)(148 * 8 + g - 1) / g));
         { KernelScope ks(K_NMI_HIST, s, (double)std::min<size_t>(n - c0 * chunk, (size_t)g * chunk)); nmi_hist_kernel<<<dim3(bpc, g), 256, 0, s>>>(a, b, n, chunk, c0, hist); }
@@ -140,4 +141,10 @@ extern "C" int ma_nmi_chunks(const uint8_t* a, const uint8_t* b, size_t n, size_
         MA_LAUNCH_CHECK("nmi kernels");
     }
     return MA_OK;
+}
+
+extern "C" int ma_nmi_chunks(const uint8_t* a, const uint8_t* b, size_t n, size_t chunk,
+                             double* scores_out, void* workspace, void* stream) {
+    if (chunk == 0) return invalid("ma_nmi_chunks: bad argument");
+    return ma_nmi_chunk_range(a, b, n, chunk, 0, (n + chunk - 1) / chunk, scores_out, workspace, stream);
 }

@@ -50,10 +50,11 @@ __device__ __forceinline__ float2 up_row(const float2* __restrict__ row, int n, 
 }
 
 __global__ void __launch_bounds__(256) pyrup_flow_kernel(const float2* __restrict__ src, int h, int w,
-                                                         float2* __restrict__ dst, int dh, int dw, float scale) {
+                                                         float2* __restrict__ dst, int dh, int dw, float scale,
+                                                         int ybeg, int yend) {
     int dx = blockIdx.x * blockDim.x + threadIdx.x;
-    int dy = blockIdx.y * blockDim.y + threadIdx.y;
-    if (dx >= dw || dy >= dh) return;
+    int dy = ybeg + blockIdx.y * blockDim.y + threadIdx.y;
+    if (dx >= dw || dy >= yend) return;
     int i = dy >> 1;
     int i2 = min(i + 1, h - 1);
     float2 r1 = up_row(src + (size_t)i * w, w, dx, scale);
@@ -90,14 +91,21 @@ extern "C" int ma_pyrdown(const void* src, size_t src_pitch, int h, int w, int d
     return MA_OK;
 }
 
-extern "C" int ma_pyrup_flow(const float* src, int h, int w, float* dst, int dh, int dw, float scale, void* stream) {
+extern "C" int ma_pyrup_flow_rows(const float* src, int h, int w, float* dst, int dh, int dw, float scale,
+                                  int row_begin, int row_end, void* stream) {
     if (!src || !dst || h <= 0 || w <= 0) return invalid("ma_pyrup_flow: bad argument");
     // cv.pyrUp accepts |dsize - 2*ssize| == dsize % 2; the reference only produces 2n and 2n-1
     if (!((dh == 2 * h || dh == 2 * h - 1) && (dw == 2 * w || dw == 2 * w - 1)) || dh <= 0 || dw <= 0)
         return invalid("ma_pyrup_flow: dstsize must be 2n or 2n-1 per axis");
-    dim3 block(32, 8), grid(ceil_div(dw, 32), ceil_div(dh, 8));
-    KernelScope ks(K_PYRUP, (cudaStream_t)stream, (double)dh * dw);
-    pyrup_flow_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const float2*)src, h, w, (float2*)dst, dh, dw, scale);
+    if (row_begin < 0 || row_end > dh || row_begin > row_end) return invalid("ma_pyrup_flow: bad row range");
+    if (row_begin == row_end) return MA_OK;
+    dim3 block(32, 8), grid(ceil_div(dw, 32), ceil_div(row_end - row_begin, 8));
+    KernelScope ks(K_PYRUP, (cudaStream_t)stream, (double)(row_end - row_begin) * dw);
+    pyrup_flow_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const float2*)src, h, w, (float2*)dst, dh, dw, scale, row_begin, row_end);
     MA_LAUNCH_CHECK("pyrup_flow_kernel");
     return MA_OK;
+}
+
+extern "C" int ma_pyrup_flow(const float* src, int h, int w, float* dst, int dh, int dw, float scale, void* stream) {
+    return ma_pyrup_flow_rows(src, h, w, dst, dh, dw, scale, 0, dh, stream);
 }

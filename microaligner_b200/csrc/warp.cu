@@ -39,10 +39,10 @@ __device__ __forceinline__ Taps make_taps(float mx, float my) {
 template <typename T>
 __global__ void __launch_bounds__(256) warp_tiles_kernel(const T* __restrict__ img, size_t img_pitch,
                                                          const float2* __restrict__ flow, TileGeom g,
-                                                         T* __restrict__ out, size_t out_pitch) {
+                                                         T* __restrict__ out, size_t out_pitch, int ybeg, int yend) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= g.w || y >= g.h) return;
+    int y = ybeg + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= g.w || y >= yend) return;
     int ti = y / g.Th, tj = x / g.Tw;
     int ty = g.ov + (y - ti * g.Th), tx = g.ov + (x - tj * g.Tw);  // tile-local pixel
     int oy = ti * g.Th - g.ov, ox = tj * g.Tw - g.ov;              // window origin in the image
@@ -79,9 +79,9 @@ __global__ void __launch_bounds__(256) warp_tiles_kernel(const T* __restrict__ i
 
 // ---- merge: pass 0 = per-tile signed max of both flows over the full window (zero padding counts)
 __global__ void __launch_bounds__(256) tile_max_kernel(const float2* __restrict__ f1, const float2* __restrict__ f2,
-                                                       TileGeom g, unsigned* __restrict__ keys) {
+                                                       TileGeom g, unsigned* __restrict__ keys, int tile0) {
     // grid: (chunks, ntiles); each block scans a slice of the window rows of one tile
-    int tile = blockIdx.y;
+    int tile = tile0 + blockIdx.y;
     int ti = tile / g.nx, tj = tile % g.nx;
     int oy = ti * g.Th - g.ov, ox = tj * g.Tw - g.ov;
     int y0 = max(oy, 0), y1 = min(oy + g.Sh, g.h);
@@ -114,10 +114,10 @@ __global__ void init_keys_kernel(unsigned* keys, int n) {
 // ABSOLUTE tile-local coordinate -f1 (quirk Q1: the reference passes map = -flow1 to cv.remap).
 __global__ void __launch_bounds__(256) merge_tiles_kernel(const float2* __restrict__ f1, const float2* __restrict__ f2,
                                                           TileGeom g, const unsigned* __restrict__ keys,
-                                                          float2* __restrict__ out) {
+                                                          float2* __restrict__ out, int ybeg, int yend) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= g.w || y >= g.h) return;
+    int y = ybeg + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= g.w || y >= yend) return;
     int ti = y / g.Th, tj = x / g.Tw;
     int tile = ti * g.nx + tj;
     size_t idx = (size_t)y * g.w + x;
@@ -155,21 +155,28 @@ __global__ void __launch_bounds__(256) merge_tiles_kernel(const float2* __restri
 
 using namespace ma;
 
-extern "C" int ma_warp_tiles(const void* img, size_t img_pitch, int dtype, const float* flow, int h, int w,
-                             int T, int ov, void* out, size_t out_pitch, void* stream) {
+extern "C" int ma_warp_tiles_rows(const void* img, size_t img_pitch, int dtype, const float* flow, int h, int w,
+                                  int T, int ov, void* out, size_t out_pitch, int row_begin, int row_end, void* stream) {
     if (!img || !flow || !out || h <= 0 || w <= 0 || T <= 0 || ov < 0) return invalid("ma_warp_tiles: bad argument");
     if (dtype != MA_U8 && dtype != MA_U16) return invalid("ma_warp_tiles: dtype must be MA_U8 or MA_U16");
     if (T + 2 * ov > 32767) return invalid("ma_warp_tiles: tile window exceeds cv.remap's int16 coordinate range");
+    if (row_begin < 0 || row_end > h || row_begin > row_end) return invalid("ma_warp_tiles: bad row range");
+    if (row_begin == row_end) return MA_OK;
     TileGeom g = make_geom(h, w, T, ov);
-    dim3 block(64, 4), grid(ceil_div(w, 64), ceil_div(h, 4));
+    dim3 block(64, 4), grid(ceil_div(w, 64), ceil_div(row_end - row_begin, 4));
     cudaStream_t s = (cudaStream_t)stream;
-    KernelScope ks(K_WARP, s, (double)h * w);
+    KernelScope ks(K_WARP, s, (double)(row_end - row_begin) * w);
     if (dtype == MA_U8)
-        warp_tiles_kernel<uint8_t><<<grid, block, 0, s>>>((const uint8_t*)img, img_pitch, (const float2*)flow, g, (uint8_t*)out, out_pitch);
+        warp_tiles_kernel<uint8_t><<<grid, block, 0, s>>>((const uint8_t*)img, img_pitch, (const float2*)flow, g, (uint8_t*)out, out_pitch, row_begin, row_end);
     else
-        warp_tiles_kernel<uint16_t><<<grid, block, 0, s>>>((const uint16_t*)img, img_pitch, (const float2*)flow, g, (uint16_t*)out, out_pitch);
+        warp_tiles_kernel<uint16_t><<<grid, block, 0, s>>>((const uint16_t*)img, img_pitch, (const float2*)flow, g, (uint16_t*)out, out_pitch, row_begin, row_end);
     MA_LAUNCH_CHECK("warp_tiles_kernel");
     return MA_OK;
+}
+
+extern "C" int ma_warp_tiles(const void* img, size_t img_pitch, int dtype, const float* flow, int h, int w,
+                             int T, int ov, void* out, size_t out_pitch, void* stream) {
+    return ma_warp_tiles_rows(img, img_pitch, dtype, flow, h, w, T, ov, out, out_pitch, 0, h, stream);
 }
 
 extern "C" size_t ma_merge_workspace_bytes(int h, int w, int T) {
@@ -178,24 +185,33 @@ extern "C" size_t ma_merge_workspace_bytes(int h, int w, int T) {
     return (size_t)g.ny * g.nx * 2 * sizeof(unsigned);
 }
 
-extern "C" int ma_merge_flows_tiles(const float* f1, const float* f2, int h, int w, int T, int ov,
-                                    float* out, void* workspace, void* stream) {
+extern "C" int ma_merge_flows_tile_rows(const float* f1, const float* f2, int h, int w, int T, int ov,
+                                        float* out, void* workspace, int tile_row_begin, int tile_row_end, void* stream) {
     if (!f1 || !f2 || !out || !workspace || h <= 0 || w <= 0 || T <= 0 || ov < 0)
         return invalid("ma_merge_flows_tiles: bad argument");
     if (T + 2 * ov > 32767) return invalid("ma_merge_flows_tiles: tile window exceeds int16 coordinate range");
     TileGeom g = make_geom(h, w, T, ov);
+    if (tile_row_begin < 0 || tile_row_end > g.ny || tile_row_begin > tile_row_end) return invalid("ma_merge_flows_tiles: bad tile-row range");
+    if (tile_row_begin == tile_row_end) return MA_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    int ntiles = g.ny * g.nx;
+    int tile0 = tile_row_begin * g.nx, ntiles = (tile_row_end - tile_row_begin) * g.nx;
+    int ybeg = tile_row_begin * g.Th, yend = std::min(tile_row_end * g.Th, h);
     unsigned* keys = (unsigned*)workspace;
     { KernelScope ks(K_SMALL, s);
-    init_keys_kernel<<<ceil_div(2 * ntiles, 256), 256, 0, s>>>(keys, 2 * ntiles); }
+    init_keys_kernel<<<ceil_div(2 * ntiles, 256), 256, 0, s>>>(keys + 2 * tile0, 2 * ntiles); }
     int chunks = max(1, min(64, (int)(((long long)g.Sh * g.Sw) / (256 * 16))));
     if (ntiles > 65535) return invalid("ma_merge_flows_tiles: too many tiles");
-    { KernelScope ks(K_MERGE_MAX, s, (double)h * w);
-    tile_max_kernel<<<dim3(chunks, ntiles), 256, 0, s>>>((const float2*)f1, (const float2*)f2, g, keys); }
-    dim3 block(64, 4), grid(ceil_div(w, 64), ceil_div(h, 4));
-    KernelScope ks(K_MERGE, s, (double)h * w);
-    merge_tiles_kernel<<<grid, block, 0, s>>>((const float2*)f1, (const float2*)f2, g, keys, (float2*)out);
+    { KernelScope ks(K_MERGE_MAX, s, (double)(yend - ybeg) * w);
+    tile_max_kernel<<<dim3(chunks, ntiles), 256, 0, s>>>((const float2*)f1, (const float2*)f2, g, keys, tile0); }
+    dim3 block(64, 4), grid(ceil_div(w, 64), ceil_div(yend - ybeg, 4));
+    KernelScope ks(K_MERGE, s, (double)(yend - ybeg) * w);
+    merge_tiles_kernel<<<grid, block, 0, s>>>((const float2*)f1, (const float2*)f2, g, keys, (float2*)out, ybeg, yend);
     MA_LAUNCH_CHECK("merge_tiles_kernel");
     return MA_OK;
+}
+
+extern "C" int ma_merge_flows_tiles(const float* f1, const float* f2, int h, int w, int T, int ov,
+                                    float* out, void* workspace, void* stream) {
+    if (h <= 0 || T <= 0) return invalid("ma_merge_flows_tiles: bad argument");
+    return ma_merge_flows_tile_rows(f1, f2, h, w, T, ov, out, workspace, 0, (h + T - 1) / T, stream);
 }

@@ -1,0 +1,252 @@
+"""Device engine of OptFlowRegistrator.register() / Warper.warp(): the reference's coarse-to-fine loop
+(optflow_reg/optflow_registrator.py:93-173) on device tensors, written once for 1..N GPUs.
+
+Sharding (parallel.Comm): at every tiled pyramid level rank r owns a contiguous band of
+tile rows.  Each stage computes only the image rows it owns; what a later stage needs beyond the band
+(tile-window overlap, the 20-row DoG halo, the rows an NMI chunk runs past the band, the rows pyrUp
+reads) is fetched from the owner with point-to-point row exchanges.  Global scalars -- DoG min/max and
+the per-chunk NMI scores -- are all-reduced, so every rank takes the same Better/Worse decision.
+Levels the reference computes untiled (max(shape)/tile_size < 2) are tiny and run replicated.
+With one rank every exchange is a no-op and the code below is simply the single-GPU path."""
+from math import log2
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import ops, parallel
+
+Range = Tuple[int, int]
+
+
+def _clip(a: int, b: int, h: int) -> Range:
+    a, b = max(a, 0), min(b, h)
+    return (a, max(a, b))
+
+
+def _union(a: Range, b: Range) -> Range:
+    return (min(a[0], b[0]), max(a[1], b[1]))
+
+
+class LevelLayout:
+    """Who owns which rows of one pyramid level."""
+
+    def __init__(self, h: int, w: int, T: int, ov: int, comm: parallel.Comm):
+        self.h, self.w, self.T, self.ov = h, w, T, ov
+        self.tiled = not (max(h, w) / T < 2)          # flow_calc.py:60-64 and similarity_scoring.py:35
+        self.ny, self.nx = -(-h // T), -(-w // T)
+        self.sharded = self.tiled and comm.world > 1
+        if self.sharded:
+            self.tile_rows = comm.tile_row_bands(self.ny)
+            self.bands = [_clip(a * T, b * T, h) for a, b in self.tile_rows]
+        else:
+            self.tile_rows = [(0, self.ny)] * comm.world
+            self.bands = [(0, h)] * comm.world
+        self.rank = comm.rank
+        self.world = comm.world
+
+    def grow(self, lo: int, hi: int) -> List[Range]:
+        """Every rank's band extended by lo rows upwards and hi rows downwards (clipped)."""
+        return [_clip(a - lo, b + hi, self.h) if b > a else (a, a) for a, b in self.bands]
+
+    @property
+    def band(self) -> Range:
+        return self.bands[self.rank]
+
+
+class Engine:
+    def __init__(self, tile_size=1000, overlap=100, num_pyr_lvl=4, num_iterations=3, use_full_res_img=False,
+                 use_dog=False, comm: Optional[parallel.Comm] = None, log: Callable[[str], None] = None):
+        self.T, self.ov = int(tile_size), int(overlap)
+        self.num_pyr_lvl, self.iters = int(num_pyr_lvl), int(num_iterations)
+        self.full_res, self.use_dog = bool(use_full_res_img), bool(use_dog)
+        self.comm = comm or parallel.get()
+        self.win = self.ov - (1 - self.ov % 2)         # optflow_registrator.py:91
+        self._log = log
+        self.decisions: List[dict] = []
+
+    def log(self, *a):
+        if self.comm.rank == 0:
+            (self._log or print)(*a)
+
+    # ------------------------------------------------------------------ building blocks
+    def pyramid(self, arr: torch.Tensor):
+        if self.num_pyr_lvl < 0:
+            raise ValueError("Number of pyramid levels cannot be less than 0")
+        if self.num_pyr_lvl == 0 and not self.full_res:
+            raise ValueError("Number of pyramid levels is 0 and use_full_res_img is False. "
+                             "Please change one of the parameters")
+        pyr, factors, cur = [], [], arr
+        for lvl in range(self.num_pyr_lvl):
+            factor = 2 ** (lvl + 1)
+            if arr.shape[0] / factor < 100 or arr.shape[1] / factor < 100:
+                break
+            cur = ops.pyr_down(cur)
+            pyr.append(cur)
+            factors.append(factor)
+        pyr.reverse()
+        factors.reverse()
+        if self.full_res:
+            pyr.append(arr)
+            factors.append(1)
+        return pyr, factors
+
+    def dog_rows(self, img: torch.Tensor, L: LevelLayout, rows: Range, banded: bool) -> torch.Tensor:
+        """uint8 DoG of `img`, valid on `rows`.  banded: img itself only exists in bands (its global
+        min/max must be reduced); otherwise img is replicated and its min/max is computed locally."""
+        if L.sharded and banded:
+            mm = self.comm.allreduce_minmax(ops.minmax_rows(img, L.band))
+        else:
+            mm = ops.minmax_rows(img, (0, L.h))
+        diff, dmm = ops.dog_diff_rows(img, mm, rows)
+        if L.sharded:
+            self.comm.allreduce_minmax(dmm)
+        out = torch.empty((L.h, L.w), dtype=torch.uint8, device=img.device)
+        return ops.dog_quantize_rows(diff, L.w, dmm, rows, out)
+
+    def warp_rows(self, img: torch.Tensor, flow: torch.Tensor, L: LevelLayout, rows: Range) -> torch.Tensor:
+        out = torch.empty_like(img)
+        return ops.warp_tiles_rows(img, flow, self.T, self.ov, rows, out)
+
+    def mi_scores(self, a: torch.Tensor, b: torch.Tensor, L: LevelLayout) -> float:
+        """mi_tiled (similarity_scoring.py:27-50)."""
+        n = a.numel()
+        if not L.tiled:
+            return float(ops.nmi_chunks(a, b, n).cpu().numpy()[0])
+        chunk = self.T * self.T
+        nchunks = -(-n // chunk)
+        scores = torch.zeros(nchunks, dtype=torch.float64, device=a.device)
+        cr = parallel.chunk_range_of_band(L.band, L.w, chunk, n) if L.sharded else (0, nchunks)
+        ops.nmi_chunk_range(a, b, chunk, cr, scores)
+        if L.sharded:
+            self.comm.allreduce_sum(scores)
+        return float(np.mean(scores.cpu().numpy()))
+
+    def pyr_up(self, flow: torch.Tensor, Ls: LevelLayout, Ld: LevelLayout, scale: float) -> torch.Tensor:
+        """cv.pyrUp(flow*scale) from level Ls to level Ld; every rank produces the rows of its Ld band."""
+        out = torch.empty((Ld.h, Ld.w, 2), dtype=torch.float32, device=flow.device)
+        if Ls.sharded:
+            need = [_clip(a // 2 - 2, (b + 1) // 2 + 2, Ls.h) if b > a else (0, 0) for a, b in Ld.bands]
+            self.comm.exchange_rows(flow, Ls.bands, need)
+        return ops.pyr_up_flow_rows(flow, (Ld.h, Ld.w), scale, Ld.band, out)
+
+    # ------------------------------------------------------------------ register()
+    def register(self, ref: torch.Tensor, mov: torch.Tensor) -> torch.Tensor:
+        comm, T, ov = self.comm, self.T, self.ov
+        ref_pyr, factors = self.pyramid(ref)
+        mov_pyr, _ = self.pyramid(mov)
+        full = LevelLayout(ref.shape[0], ref.shape[1], T, ov, comm)
+        layouts = [LevelLayout(p.shape[0], p.shape[1], T, ov, comm) for p in ref_pyr]
+        num_lvl = len(factors)
+        self.decisions = []
+        m_flow, m_layout = None, None
+
+        for lvl, factor in enumerate(factors):
+            self.log("Pyramid factor", factor)
+            L = layouts[lvl]
+            B = L.band
+            halo = ov + (20 if self.use_dog else 0)
+            over = -(-T * T // L.w) + 1 if L.tiled else 0          # rows an NMI chunk may run past the band
+            gate_rows = _clip(B[0], B[1] + over, L.h) if L.sharded else (0, L.h)
+            win_rows = _clip(B[0] - ov, B[1] + ov, L.h) if L.sharded else (0, L.h)
+            if B[1] <= B[0]:                                       # more ranks than tile rows: nothing to do here
+                gate_rows = win_rows = (B[0], B[0])
+
+            mov_l = mov_pyr[lvl]
+            mov_banded = False
+            if lvl > 0:
+                if L.sharded:
+                    comm.exchange_rows(m_flow, L.bands, L.grow(ov, ov))      # merge reads tile windows
+                mov_l = self.warp_rows(mov_l, m_flow, L, B)
+                mov_banded = L.sharded
+                if L.sharded:
+                    comm.exchange_rows(mov_l, L.bands, L.grow(halo, halo))
+
+            # the reference DoG image serves the flow (if use_dog) and the gate (always)
+            ref_dog_rows = _union(gate_rows, win_rows) if self.use_dog else gate_rows
+            ref_dog = self.dog_rows(ref_pyr[lvl], L, ref_dog_rows, banded=False)
+            fb_ref = ref_dog if self.use_dog else ref_pyr[lvl]
+            fb_mov = self.dog_rows(mov_l, L, win_rows, banded=mov_banded) if self.use_dog else mov_l
+            this_flow = torch.empty((L.h, L.w, 2), dtype=torch.float32, device=ref.device)
+            if L.tiled:
+                tr = L.tile_rows[L.rank]
+                ops.farneback_tiles(fb_mov, fb_ref, T, ov, self.win, self.iters, (tr[0] * L.nx, tr[1] * L.nx), out=this_flow)
+            else:
+                ops.farneback_tiles(fb_mov, fb_ref, 0, 0, self.win, self.iters, out=this_flow)
+            del fb_mov, fb_ref
+            if L.sharded:
+                comm.exchange_rows(this_flow, L.bands, L.grow(ov, ov))
+
+            warped = self.warp_rows(mov_l, this_flow, L, B)
+            del mov_l
+            if L.sharded:
+                comm.exchange_rows(warped, L.bands, L.grow(20, over + 20))
+            after = self.mi_scores(ref_dog, self.dog_rows(warped, L, gate_rows, banded=L.sharded), L)
+            del warped
+            before = self.mi_scores(ref_dog, self.dog_rows(mov_pyr[lvl], L, gate_rows, banded=False), L)
+            del ref_dog
+            self.log("    MI score after:", after, "| MI score before:", before)
+            better = after > before
+            self.decisions.append(dict(factor=factor, mi_after=after, mi_before=before, better=better))
+            Ln = layouts[lvl + 1] if lvl + 1 < num_lvl else None
+
+            if better:
+                self.log("    Better alignment than before")
+                if lvl == 0:
+                    if num_lvl > 1:
+                        m_flow, m_layout = self.pyr_up(this_flow, L, Ln, 2.0), Ln
+                    else:
+                        m_flow, m_layout = self._upscale_to_full(this_flow, L, full, factor)
+                elif lvl == num_lvl - 1:
+                    merged = ops.merge_flows_tile_rows(m_flow, this_flow, T, ov, L.tile_rows[L.rank], torch.empty_like(this_flow))
+                    m_flow, m_layout = merged, L
+                    if not self.full_res:
+                        m_flow, m_layout = self._upscale_to_full(merged, L, full, factor)
+                else:
+                    merged = ops.merge_flows_tile_rows(m_flow, this_flow, T, ov, L.tile_rows[L.rank], torch.empty_like(this_flow))
+                    m_flow, m_layout = self.pyr_up(merged, L, Ln, 2.0), Ln
+            else:
+                self.log("    Worse alignment than before")
+                if lvl == 0:
+                    shape = (Ln.h, Ln.w) if num_lvl > 1 else tuple(mov.shape)
+                    m_flow = torch.zeros(shape + (2,), dtype=torch.float32, device=ref.device)
+                    m_layout = Ln if num_lvl > 1 else full
+                elif lvl == num_lvl - 1:
+                    if not self.full_res:
+                        m_flow, m_layout = self.pyr_up(m_flow, L, full, 2.0), full
+                else:
+                    m_flow, m_layout = self.pyr_up(m_flow, L, Ln, 4.0), Ln
+            del this_flow
+
+        if m_flow is None:
+            # no pyramid level at all: the reference fails on its unbound local (optflow_registrator.py:173)
+            raise UnboundLocalError("cannot access local variable 'm_flow' where it is not associated with a value")
+        if m_layout is not None and m_layout.sharded:
+            comm.gather_rows(m_flow, m_layout.bands)
+        return m_flow
+
+    def _upscale_to_full(self, flow: torch.Tensor, L: LevelLayout, full: LevelLayout, factor: int):
+        """_upscale_flow_to_full_res (optflow_registrator.py:204-215): NOT scaled by 2 (quirk Q2)."""
+        if abs(flow.shape[0] - full.h) <= 1:
+            return flow, L
+        num_lvls = int(log2(factor))
+        out, lay = flow, L
+        for i in range(num_lvls):
+            if i == num_lvls - 1:
+                out, lay = self.pyr_up(flow, L, full, 1.0), full
+            else:  # unreachable for contiguous factors; kept for parity with the reference's loop
+                mid = LevelLayout(2 * flow.shape[0], 2 * flow.shape[1], self.T, self.ov, self.comm)
+                out, lay = self.pyr_up(flow, L, mid, 1.0), mid
+        return out, lay
+
+    # ------------------------------------------------------------------ warp()
+    def warp(self, img: torch.Tensor, flow: torch.Tensor) -> torch.Tensor:
+        """Warper.warp (warper.py:37-76); with several ranks each warps its band and the image is gathered."""
+        L = LevelLayout(img.shape[0], img.shape[1], self.T, self.ov, self.comm)
+        if self.comm.world > 1 and L.ny >= 2:
+            tr = self.comm.tile_row_bands(L.ny)
+            bands = [_clip(a * self.T, b * self.T, L.h) for a, b in tr]
+            out = torch.empty_like(img)
+            ops.warp_tiles_rows(img, flow, self.T, self.ov, bands[self.comm.rank], out)
+            return self.comm.gather_rows(out, bands)
+        return ops.warp_tiles(img, flow, self.T, self.ov)

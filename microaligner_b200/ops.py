@@ -208,3 +208,68 @@ def zmip_normalize_u8(pages: Sequence[torch.Tensor]) -> torch.Tensor:
     check(lib.ma_zmip_normalize_u8(arr, len(pages), w * pages[0].element_size(), _code(pages[0]), h, w, out.data_ptr(), w,
                                    ws.data_ptr(), _stream()), "ma_zmip_normalize_u8")
     return out
+
+
+# --------------------------------------------------------------------------------- row-range variants (row-sharded engine)
+def warp_tiles_rows(img, flow, tile_size, overlap, rows, out):
+    """Rows [rows[0], rows[1]) of Warper.warp written into `out` (full-size buffer)."""
+    h, w = img.shape
+    es = img.element_size()
+    check(lib.ma_warp_tiles_rows(img.data_ptr(), w * es, _code(img), flow.data_ptr(), h, w, int(tile_size), int(overlap),
+                                 out.data_ptr(), w * es, int(rows[0]), int(rows[1]), _stream()), "ma_warp_tiles_rows")
+    return out
+
+
+def pyr_up_flow_rows(flow, dsize_hw, scale, rows, out):
+    h, w, _ = flow.shape
+    check(lib.ma_pyrup_flow_rows(flow.data_ptr(), h, w, out.data_ptr(), int(dsize_hw[0]), int(dsize_hw[1]), float(scale),
+                                 int(rows[0]), int(rows[1]), _stream()), "ma_pyrup_flow_rows")
+    return out
+
+
+def merge_flows_tile_rows(f1, f2, tile_size, overlap, tile_rows, out):
+    h, w, _ = f1.shape
+    ws = _bytes(lib.ma_merge_workspace_bytes(h, w, int(tile_size)), f1.device)
+    check(lib.ma_merge_flows_tile_rows(f1.data_ptr(), f2.data_ptr(), h, w, int(tile_size), int(overlap), out.data_ptr(),
+                                       ws.data_ptr(), int(tile_rows[0]), int(tile_rows[1]), _stream()), "ma_merge_flows_tile_rows")
+    return out
+
+
+def minmax_rows(img, rows):
+    """[min, max] (float32 device tensor) of image rows [rows[0], rows[1])."""
+    h, w = img.shape
+    out = torch.empty(2, dtype=torch.float32, device=img.device)
+    if rows[1] <= rows[0]:
+        out[0], out[1] = float("inf"), float("-inf")
+        return out
+    es = img.element_size()
+    check(lib.ma_minmax(img.data_ptr() + int(rows[0]) * w * es, w * es, _code(img), int(rows[1] - rows[0]), w, out.data_ptr(),
+                        _stream()), "ma_minmax")
+    return out
+
+
+def dog_diff_rows(img, src_minmax, rows):
+    """Rows of the un-normalised difference of Gaussians + their [min, max]; see ma_dog_diff_rows."""
+    h, w = img.shape
+    wp = lib.ma_dog_diff_pitch_floats(w)
+    diff = torch.empty((h, wp), dtype=torch.float32, device=img.device)
+    dmm = torch.empty(2, dtype=torch.float32, device=img.device)
+    ws = _bytes(lib.ma_dog_workspace_bytes(h, w), img.device)
+    check(lib.ma_dog_diff_rows(img.data_ptr(), w * img.element_size(), _code(img), h, w, src_minmax.data_ptr(), int(rows[0]),
+                               int(rows[1]), diff.data_ptr(), dmm.data_ptr(), ws.data_ptr(), _stream()), "ma_dog_diff_rows")
+    return diff, dmm
+
+
+def dog_quantize_rows(diff, w, diff_minmax, rows, out):
+    h = diff.shape[0]
+    check(lib.ma_dog_quantize_rows(diff.data_ptr(), h, int(w), diff_minmax.data_ptr(), int(rows[0]), int(rows[1]),
+                                   out.data_ptr(), int(w), _stream()), "ma_dog_quantize_rows")
+    return out
+
+
+def nmi_chunk_range(a, b, chunk, chunk_range, scores):
+    n = a.numel()
+    ws = _bytes(lib.ma_nmi_workspace_bytes(n, int(chunk)), a.device)
+    check(lib.ma_nmi_chunk_range(a.data_ptr(), b.data_ptr(), n, int(chunk), int(chunk_range[0]), int(chunk_range[1]),
+                                 scores.data_ptr(), ws.data_ptr(), _stream()), "ma_nmi_chunk_range")
+    return scores

@@ -14,9 +14,9 @@ from typing import List, Tuple
 import numpy as np
 import torch
 
-from .. import ops
+from .. import ops, parallel
+from ..engine import Engine
 from ..shared_modules.img_checks import check_img_dims_match, check_img_is_2d_grey, check_img_is_provided
-from ..shared_modules.similarity_scoring import check_if_higher_similarity
 from .flow_calc import TileFlowCalc
 from .warper import Warper
 
@@ -135,60 +135,12 @@ class OptFlowRegistrator:
 
         self._init_tile_flow_calc()
         self._init_warper()
-        tfc = self._tile_flow_calc
 
         ref = ops.to_device(self._ref_img)
         mov = ops.to_device(self._mov_img, ref.device)
         self._full_shape = tuple(ref.shape)
-        ref_pyr, factors = self._generate_img_pyr(ref)
-        mov_pyr, _ = self._generate_img_pyr(mov)
-        self.decisions = []
-
-        num_lvl = len(factors)
-        for lvl, factor in enumerate(factors):
-            print("Pyramid factor", factor)
-            mov_this_lvl = mov_pyr[lvl]
-            if lvl > 0:
-                mov_this_lvl = self._warp(mov_this_lvl, m_flow)
-            ref_dog = self.dog(ref_pyr[lvl], True)  # needed by the gate in any case
-            tfc.ref_img = ref_dog if self.use_dog else ref_pyr[lvl]
-            tfc.mov_img = self.dog(mov_this_lvl, self.use_dog)
-            this_flow = tfc.calc_flow()
-
-            mov_this_lvl = self._warp(mov_this_lvl, this_flow)
-            is_higher_similarity = check_if_higher_similarity(
-                ref_dog, self.dog(mov_this_lvl, True), self.dog(mov_pyr[lvl], True), self.tile_size)
-            del ref_dog, mov_this_lvl
-            better = any(is_higher_similarity)
-            self.decisions.append(dict(factor=factor, better=better))
-
-            if better:
-                print("    Better alignment than before")
-                if lvl == 0:
-                    if num_lvl > 1:
-                        m_flow = ops.pyr_up_flow(this_flow, mov_pyr[lvl + 1].shape, 2.0)
-                    else:
-                        m_flow = self._upscale_flow_to_full_res(this_flow, factor)
-                elif lvl == num_lvl - 1:
-                    m_flow = self._merge_list_of_flows([m_flow, this_flow])
-                    if not self.use_full_res_img:
-                        m_flow = self._upscale_flow_to_full_res(m_flow, factor)
-                else:
-                    m_flow = self._merge_list_of_flows([m_flow, this_flow])
-                    m_flow = ops.pyr_up_flow(m_flow, mov_pyr[lvl + 1].shape, 2.0)
-                del this_flow
-            else:
-                print("    Worse alignment than before")
-                if lvl == 0:
-                    shape = tuple(mov_pyr[lvl + 1].shape) if num_lvl > 1 else tuple(mov.shape)
-                    m_flow = torch.zeros(shape + (2,), dtype=torch.float32, device=ref.device)
-                elif lvl == num_lvl - 1:
-                    if not self.use_full_res_img:
-                        m_flow = ops.pyr_up_flow(m_flow, mov.shape, 2.0)
-                else:
-                    m_flow = ops.pyr_up_flow(m_flow, mov_pyr[lvl + 1].shape, 4.0)
-
-        del mov_pyr, ref_pyr
-        # no pyramid level at all (image side / 2 < 100 and no full-res): the reference dies with
-        # UnboundLocalError on m_flow (optflow_registrator.py:173); the name lookup below does the same
+        eng = Engine(self.tile_size, self.overlap, self.num_pyr_lvl, self.num_iterations, self.use_full_res_img,
+                     self.use_dog, comm=parallel.get())
+        m_flow = eng.register(ref, mov)     # the coarse-to-fine loop, sharded over the ranks of parallel.get()
+        self.decisions = eng.decisions
         return ops.to_host(m_flow) if host_result else m_flow

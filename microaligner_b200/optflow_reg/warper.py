@@ -9,7 +9,8 @@ otherwise a CUDA tensor (device-resident hand-off inside the pipeline)."""
 import numpy as np
 import torch
 
-from .. import ops
+from .. import ops, parallel
+from ..engine import Engine
 
 
 class Warper:
@@ -26,5 +27,5 @@ class Warper:
         flow = ops.to_device(self.flow, img.device)
         self.image = np.array([])
         self.flow = np.array([])
-        out = ops.warp_tiles(img, flow, self.tile_size, self.overlap)
+        out = Engine(self.tile_size, self.overlap, comm=parallel.get()).warp(img, flow)
         return ops.to_host(out) if host_result else out

@@ -1,0 +1,158 @@
+"""Row-band sharding of the registration path across the GPUs of one node.
+
+One process per GPU (torchrun); `init(group)` installs the process group (NCCL over NVLink on the GPU
+box, gloo in the CPU tests).  The path shards by tile rows: every stage computes the
+image rows it owns, halo rows are exchanged point-to-point, the few global scalars (DoG min/max, NMI
+chunk scores) are all-reduced, and the final flow / image is gathered band by band.  With a world of 1
+every function here is a no-op, so the single-GPU path runs the very same engine code."""
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+Range = Tuple[int, int]
+
+
+def split_even(n: int, parts: int) -> List[Range]:
+    """Contiguous, as-even-as-possible partition of range(n) into `parts` (possibly empty) ranges."""
+    base, rem = divmod(n, parts)
+    out, a = [], 0
+    for r in range(parts):
+        b = a + base + (1 if r < rem else 0)
+        out.append((a, b))
+        a = b
+    return out
+
+
+def intersect(a: Range, b: Range) -> Range:
+    lo, hi = max(a[0], b[0]), min(a[1], b[1])
+    return (lo, hi) if hi > lo else (lo, lo)
+
+
+def subtract(a: Range, b: Range) -> List[Range]:
+    """a minus b as up to two ranges."""
+    out = []
+    if a[1] <= a[0]:
+        return out
+    i = intersect(a, b)
+    if i[1] <= i[0]:
+        return [a]
+    if a[0] < i[0]:
+        out.append((a[0], i[0]))
+    if i[1] < a[1]:
+        out.append((i[1], a[1]))
+    return out
+
+
+def transfer_plan(owned: Sequence[Range], need: Sequence[Range]) -> List[Tuple[int, int, Range]]:
+    """(src, dst, rows) for every block of rows rank `dst` needs but does not own. `owned` must be disjoint."""
+    plan = []
+    for dst, nd in enumerate(need):
+        for miss in subtract(nd, owned[dst]):
+            for src, ow in enumerate(owned):
+                if src == dst:
+                    continue
+                rows = intersect(miss, ow)
+                if rows[1] > rows[0]:
+                    plan.append((src, dst, rows))
+    return plan
+
+
+def chunk_range_of_band(band: Range, w: int, chunk: int, n: int) -> Range:
+    """NMI chunks (runs of `chunk` row-major elements of an image of width w, n elements in total)
+    whose first element lies in image rows [band)."""
+    c0 = -(-(band[0] * w) // chunk)
+    c1 = -(-(min(band[1] * w, n)) // chunk)
+    return (c0, max(c0, c1))
+
+
+class Comm:
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if group is not None else 1
+        self.rank = dist.get_rank(group) if group is not None else 0
+        self.backend = dist.get_backend(group) if group is not None else None
+
+    # -- layout ---------------------------------------------------------------------------------
+    def tile_row_bands(self, ny: int) -> List[Range]:
+        return split_even(ny, self.world)
+
+    # -- data movement --------------------------------------------------------------------------
+    def _wire(self, t: torch.Tensor) -> torch.Tensor:
+        return t.view(torch.int16) if t.dtype == torch.uint16 else t
+
+    def exchange_rows(self, t: torch.Tensor, owned: Sequence[Range], need: Sequence[Range]):
+        """Make rows need[rank] of `t` valid on this rank, given that rank q holds rows owned[q]."""
+        if self.world == 1:
+            return t
+        plan = transfer_plan(owned, need)
+        mine = [p for p in plan if self.rank in (p[0], p[1])]
+        if not mine:
+            return t
+        tw = self._wire(t)
+        stage_cpu = self.backend == "gloo" and t.is_cuda
+        ops, recvs = [], []
+        for src, dst, (a, b) in mine:
+            view = tw[a:b]
+            if src == self.rank:
+                buf = view.cpu() if stage_cpu else view
+                ops.append(dist.P2POp(dist.isend, buf, dst, group=self.group))
+            else:
+                buf = torch.empty(view.shape, dtype=view.dtype, device="cpu") if stage_cpu else view
+                ops.append(dist.P2POp(dist.irecv, buf, src, group=self.group))
+                if stage_cpu:
+                    recvs.append((view, buf))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        for view, buf in recvs:
+            view.copy_(buf)
+        return t
+
+    def gather_rows(self, t: torch.Tensor, owned: Sequence[Range]):
+        """Every rank ends up with all rows of `t` (rank q contributes rows owned[q])."""
+        if self.world == 1:
+            return t
+        full = (0, t.shape[0])
+        return self.exchange_rows(t, owned, [full] * self.world)
+
+    def allreduce_minmax(self, mm: torch.Tensor):
+        """mm = [min, max] float32 (device); reduced in place over the group."""
+        if self.world == 1:
+            return mm
+        v = torch.stack([-mm[0], mm[1]])
+        v = self._allreduce(v, dist.ReduceOp.MAX)
+        mm[0], mm[1] = -v[0], v[1]
+        return mm
+
+    def _allreduce(self, t: torch.Tensor, op):
+        if self.backend == "gloo" and t.is_cuda:      # CPU-staged: only the 1-GPU multi-rank tests take this path
+            c = t.cpu()
+            dist.all_reduce(c, op=op, group=self.group)
+            t.copy_(c)
+        else:
+            dist.all_reduce(t, op=op, group=self.group)
+        return t
+
+    def allreduce_sum(self, t: torch.Tensor):
+        if self.world > 1:
+            self._allreduce(t, dist.ReduceOp.SUM)
+        return t
+
+    def broadcast(self, t: torch.Tensor, src: int = 0):
+        if self.world > 1:
+            dist.broadcast(self._wire(t), src=src, group=self.group)
+        return t
+
+
+_COMM = Comm(None)
+
+
+def init(group=None) -> Comm:
+    """Install the process group the engine shards over (None = single process)."""
+    global _COMM
+    _COMM = Comm(group)
+    return _COMM
+
+
+def get() -> Comm:
+    return _COMM
