@@ -172,10 +172,19 @@ def run_b200(args):
         parallel.init(dist.group.WORLD)
 
     S = args.size
-    ref_h = torch.empty((S, S), dtype=torch.uint16, pin_memory=True).numpy()
-    mov_h = torch.empty((S, S), dtype=torch.uint16, pin_memory=True).numpy()
-    synth_pair_large(S, S, seed=0, out=(ref_h, mov_h))
-    ref_d, mov_d = torch.from_numpy(ref_h).to(dev), torch.from_numpy(mov_h).to(dev)
+    comm = parallel.get() if world > 1 else None
+    if rank == 0:
+        ref_h = torch.empty((S, S), dtype=torch.uint16, pin_memory=True).numpy()
+        mov_h = torch.empty((S, S), dtype=torch.uint16, pin_memory=True).numpy()
+        synth_pair_large(S, S, seed=0, out=(ref_h, mov_h))
+        ref_d, mov_d = torch.from_numpy(ref_h).to(dev), torch.from_numpy(mov_h).to(dev)
+    else:
+        ref_h = mov_h = None
+        ref_d = torch.empty((S, S), dtype=torch.uint16, device=dev)
+        mov_d = torch.empty((S, S), dtype=torch.uint16, device=dev)
+    if world > 1:  # inputs are replicated on every GPU; only computed data crosses NVLink afterwards
+        comm.broadcast(ref_d, 0)
+        comm.broadcast(mov_d, 0)
 
     reg, wrp = OptFlowRegistrator(), Warper()
     for k, v in PARAMS.items():
@@ -189,10 +198,23 @@ def run_b200(args):
         return wrp.warp()
 
     def step_host():
-        reg.ref_img, reg.mov_img = ref_h, mov_h
+        if world == 1:  # the drop-in numpy API
+            reg.ref_img, reg.mov_img = ref_h, mov_h
+            flow = reg.register()
+            wrp.image, wrp.flow = mov_h, flow
+            return wrp.warp()
+        # N ranks: rank 0 owns the host arrays; upload + NVLink broadcast, sharded step, rank 0 downloads
+        r = ops.to_device(ref_h, dev) if rank == 0 else torch.empty_like(ref_d)
+        m = ops.to_device(mov_h, dev) if rank == 0 else torch.empty_like(mov_d)
+        comm.broadcast(r, 0)
+        comm.broadcast(m, 0)
+        reg.ref_img, reg.mov_img = r, m
         flow = reg.register()
-        wrp.image, wrp.flow = mov_h, flow
-        return wrp.warp()
+        wrp.image, wrp.flow = m, flow
+        out = wrp.warp()
+        if rank == 0:
+            return ops.to_host(flow), ops.to_host(out)
+        return None
 
     def barrier():
         if world > 1:
@@ -233,8 +255,11 @@ def run_b200(args):
     value = px / (ms_dev * 1e-3) / 1e6
     e2e_val = px / (ms_e2e * 1e-3) / 1e6
     img_b, flow_b = px * 2, px * 8
-    h2d = 2 * img_b + img_b + flow_b   # register(ref, mov) + Warper(image, flow)
-    d2h = flow_b + img_b               # flow returned by register(), warped image
+    if world == 1:
+        h2d = 2 * img_b + img_b + flow_b   # register(ref, mov) + Warper(image, flow)
+    else:
+        h2d = 2 * img_b                    # rank 0 uploads ref, mov; the flow stays on the devices
+    d2h = flow_b + img_b                   # flow returned by register(), warped image
 
     if rank != 0:
         if world > 1:
@@ -269,9 +294,11 @@ def run_b200(args):
     line = {
         "metric": "Mpixel/s registered (Farneback flow + warp)", "value": value, "unit": "Mpx/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong",
+        "parallelism": f"tile-row bands over {world} GPU(s), P2P halo exchange + scalar all-reduces (NCCL)",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
         "e2e": {"value": e2e_val, "unit": "Mpx/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "OptFlowRegistrator.register() + Warper.warp() on page-locked numpy arrays"},
+                "api": "OptFlowRegistrator.register() + Warper.warp() on page-locked numpy arrays" if world == 1 else
+                       "rank 0: page-locked numpy in -> H2D -> NVLink broadcast -> sharded register()+warp() -> D2H of flow and image"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         "kernels": {k: {kk: round(vv, 4) for kk, vv in v.items()} for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms_per_step"])},
     }
@@ -291,6 +318,12 @@ def run_b200(args):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: everything else any library prints at fd level (NCCL's version
+    # banner, torch warnings) is routed to stderr for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -304,6 +337,7 @@ def main():
         run_reference(args)
     else:
         run_b200(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

@@ -79,7 +79,8 @@ class Comm:
 
     # -- data movement --------------------------------------------------------------------------
     def _wire(self, t: torch.Tensor) -> torch.Tensor:
-        return t.view(torch.int16) if t.dtype == torch.uint16 else t
+        # NCCL (torch) has no 16-bit integer type: uint16 images travel as bytes, row slicing is unaffected
+        return t.view(torch.uint8) if t.dtype == torch.uint16 else t
 
     def exchange_rows(self, t: torch.Tensor, owned: Sequence[Range], need: Sequence[Range]):
         """Make rows need[rank] of `t` valid on this rank, given that rank q holds rows owned[q]."""

@@ -63,7 +63,7 @@ def _worker(rank, world, port, h, tmp):
         assert torch.equal(t[a:b], truth[a:b])
         if a > 0:
             assert (t[:a] == -1).all()
-        # uint16 rides the wire as int16
+        # uint16 rides the wire as bytes
         u = torch.zeros((h, 5), dtype=torch.uint16)
         u[mine[0]:mine[1]] = 40000 + rank
         comm.gather_rows(u, bands)
