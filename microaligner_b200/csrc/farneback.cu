@@ -47,11 +47,13 @@ struct FbBatch {
     int Sp;           // row pitch (floats) of the R0 / R1 / M planes ([y][x])
     int SpT;          // row pitch (floats) of the transposed V planes ([x][y])
     size_t plane;     // floats per plane = max(Sh * Sp, Sw * SpT)
-    float* ws;        // workspace base: per slot 20 planes [R0 x5][R1 x5][M x5][V^T x5]
+    float* ws;        // workspace base: per slot 22 planes [R0 x5][R1 x5][M x5][V^T x5][flow x2]
 };
 
-__device__ __forceinline__ float* slot_plane(const FbBatch& b, int slot, int which /*0 R0,1 R1,2 M,3 V*/, int c) {
-    return b.ws + ((size_t)slot * 20 + which * 5 + c) * b.plane;
+constexpr int kSlotPlanes = 22;  // R0 x5, R1 x5, M x5, V^T x5, tile flow (float2 = 2 planes)
+
+__device__ __forceinline__ float* slot_plane(const FbBatch& b, int slot, int which /*0 R0,1 R1,2 M,3 V^T,4 flow*/, int c) {
+    return b.ws + ((size_t)slot * kSlotPlanes + which * 5 + c) * b.plane;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -368,7 +370,7 @@ __global__ void __launch_bounds__(256) fb_blur_v_kernel(const __grid_constant__ 
     __syncthreads();
     if (threadIdx.x == 0) {
         mbar_expect_tx(&bar, rows * kRowF * sizeof(float));
-        tma_load_3d(smem, &mapM, x0, y0 - m, slot * 20 + 10 + c, &bar);
+        tma_load_3d(smem, &mapM, x0, y0 - m, slot * kSlotPlanes + 10 + c, &bar);
     }
     mbar_wait(&bar, 0);
     replicate_edges(smem, rows, y0 - m, Sh);
@@ -434,7 +436,7 @@ __global__ void __launch_bounds__(256, 2) fb_blur_h_kernel(const __grid_constant
     if (threadIdx.x == 0) {
         for (int c = 0; c < 2; ++c) {
             mbar_expect_tx(&bars[c], box_bytes);
-            tma_load_3d(buf[c], &mapVT, y0, x0 - m, slot * 20 + 15 + c, &bars[c]);
+            tma_load_3d(buf[c], &mapVT, y0, x0 - m, slot * kSlotPlanes + 15 + c, &bars[c]);
         }
     }
     const u64 nz = *reinterpret_cast<const u64*>(&cst.negzero2);
@@ -448,7 +450,7 @@ __global__ void __launch_bounds__(256, 2) fb_blur_h_kernel(const __grid_constant
         __syncthreads();  // buffer c&1 is free again
         if (c + 2 < 5 && threadIdx.x == 0) {
             mbar_expect_tx(&bars[c & 1], box_bytes);
-            tma_load_3d(buf[c & 1], &mapVT, y0, x0 - m, slot * 20 + 15 + c + 2, &bars[c & 1]);
+            tma_load_3d(buf[c & 1], &mapVT, y0, x0 - m, slot * kSlotPlanes + 15 + c + 2, &bars[c & 1]);
         }
     }
     // 2x2 solve in f64 (FarnebackUpdateFlow_GaussianBlur), flow staged as [x][y]
@@ -475,27 +477,42 @@ __global__ void __launch_bounds__(256, 2) fb_blur_h_kernel(const __grid_constant
         }
     }
     __syncthreads();
-    // epilogue: lanes <-> x
+    // epilogue: lanes <-> x.  Last iteration: scatter the tile centre into the stitched flow.  Otherwise the
+    // flow goes to the tile's flow plane and fb_update_kernel recomputes M from it: UpdateMatrices is a
+    // latency-bound gather (flow -> address -> 20 R1 values) that a separate, fully occupied pointwise
+    // kernel hides far better than the 16-warp convolution CTA can (ncu: 56 % of this kernel's stall
+    // samples sat on those loads when it was fused here); the price is 16 B/px of extra traffic.
     const int tile = b.tile0 + slot;
     const int ti = tile / g.nx, tj = tile % g.nx;
     const int cx = threadIdx.x & 63, x = x0 + cx;
-    if (x < Sw) {
-        for (int r = threadIdx.x >> 6; r < kRowF; r += 4) {
-            int y = y0 + r;
-            if (y >= Sh) break;
-            float2 f = fl[cx * kFlowPitch + r];
-            if (last_iter) {
-                int cy = y - g.ov, cxx = x - g.ov;
-                if ((unsigned)cy < (unsigned)g.Th && (unsigned)cxx < (unsigned)g.Tw) {
-                    int gy = ti * g.Th + cy, gx = tj * g.Tw + cxx;
-                    if (gy < g.h && gx < g.w) flow_out[(size_t)gy * g.w + gx] = f;
-                }
-            } else {
-                update_matrices_px(slot_plane(b, slot, 0, 0), slot_plane(b, slot, 1, 0), b.plane, b.Sp, Sw, Sh,
-                                   x, y, f.x, f.y, slot_plane(b, slot, 2, 0));
+    if (x >= Sw) return;
+    float2* __restrict__ F = reinterpret_cast<float2*>(slot_plane(b, slot, 4, 0));
+    for (int r = threadIdx.x >> 6; r < kRowF; r += 4) {
+        int y = y0 + r;
+        if (y >= Sh) break;
+        float2 f = fl[cx * kFlowPitch + r];
+        if (last_iter) {
+            int cy = y - g.ov, cxx = x - g.ov;
+            if ((unsigned)cy < (unsigned)g.Th && (unsigned)cxx < (unsigned)g.Tw) {
+                int gy = ti * g.Th + cy, gx = tj * g.Tw + cxx;
+                if (gy < g.h && gx < g.w) flow_out[(size_t)gy * g.w + gx] = f;
             }
+        } else {
+            F[(size_t)y * b.Sp + x] = f;
         }
     }
+}
+
+// K2 (iterations > 0): M = UpdateMatrices(R0, R1, flow), one thread per tile pixel, everything coalesced
+// except the bilinear gather of R1 around (x + dx, y + dy).
+__global__ void __launch_bounds__(256) fb_update_kernel(FbBatch b) {
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int slot = blockIdx.z;
+    if (x >= b.g.Sw || y >= b.g.Sh) return;
+    const float2 f = __ldg(reinterpret_cast<const float2*>(slot_plane(b, slot, 4, 0)) + (size_t)y * b.Sp + x);
+    update_matrices_px(slot_plane(b, slot, 0, 0), slot_plane(b, slot, 1, 0), b.plane, b.Sp, b.g.Sw, b.g.Sh,
+                       x, y, f.x, f.y, slot_plane(b, slot, 2, 0));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -596,7 +613,7 @@ static inline size_t plane_floats(const TileGeom& g) {
 extern "C" size_t ma_farneback_workspace_bytes(int h, int w, int T, int ov, int n_batch) {
     if (h <= 0 || w <= 0 || n_batch <= 0) return 0;
     TileGeom g = make_geom(h, w, T, ov);
-    return (size_t)n_batch * 20 * plane_floats(g) * sizeof(float);
+    return (size_t)n_batch * kSlotPlanes * plane_floats(g) * sizeof(float);
 }
 
 extern "C" int ma_farneback_tiles(const void* mov, const void* ref, size_t pitch, int dtype, int h, int w,
@@ -615,7 +632,7 @@ extern "C" int ma_farneback_tiles(const void* mov, const void* ref, size_t pitch
     int Sp = plane_pitch(g.Sw), SpT = plane_pitch(g.Sh);
     size_t plane = plane_floats(g);
     if ((reinterpret_cast<uintptr_t>(workspace) & 127) != 0) return invalid("ma_farneback_tiles: workspace must be 128-byte aligned");
-    size_t slot_bytes = 20 * plane * sizeof(float);
+    size_t slot_bytes = kSlotPlanes * plane * sizeof(float);
     int cap = (int)std::min<size_t>(workspace_bytes / slot_bytes, 4096);
     if (cap < 1) {
         set_error("ma_farneback_tiles: workspace smaller than one tile slot");
@@ -648,7 +665,7 @@ extern "C" int ma_farneback_tiles(const void* mov, const void* ref, size_t pitch
             fb_polyexp_kernel<uint16_t><<<pg, 256, 0, s>>>((const uint16_t*)mov, (const uint16_t*)ref, pitch, b, cst); }
         // TMA descriptors over this batch's planes: M as [plane][y][x], V^T as [plane][x][y]
         CUtensorMap mapM, mapVT;
-        uint64_t nplanes = (uint64_t)b.ntiles * 20;
+        uint64_t nplanes = (uint64_t)b.ntiles * kSlotPlanes;
         if (!make_plane_map(&mapM, b.ws, g.Sw, g.Sh, nplanes, (uint64_t)Sp * 4, plane * 4, kRowF, vout + 2 * m) ||
             !make_plane_map(&mapVT, b.ws, g.Sh, g.Sw, nplanes, (uint64_t)SpT * 4, plane * 4, kRowF, kStep + 2 * m)) {
             set_error("ma_farneback_tiles: cuTensorMapEncodeTiled failed");
@@ -662,6 +679,10 @@ extern "C" int ma_farneback_tiles(const void* mov, const void* ref, size_t pitch
             { KernelScope ks(K_BLUR_H, s, tpx);
             fb_blur_h_kernel<<<dim3(ceil_div(g.Sh, kRowF), ceil_div(g.Sw, kStep), b.ntiles), 256, h_smem, s>>>(
                 mapVT, b, cst, it == iters - 1, (float2*)flow_out); }
+            if (it < iters - 1) {
+                KernelScope ks(K_UPDATE0, s, tpx);
+                fb_update_kernel<<<dim3(ceil_div(g.Sw, 64), ceil_div(g.Sh, 4), b.ntiles), 256, 0, s>>>(b);
+            }
         }
         MA_LAUNCH_CHECK("farneback kernels");
     }

@@ -207,6 +207,16 @@ def dog(img: np.ndarray, low_sigma: float = 5, high_sigma: float = 9) -> np.ndar
     return np.clip(np.rint(q), 0, 255).astype(np.uint8)
 
 
+def normalize_minmax_u8(img: np.ndarray) -> np.ndarray:
+    """cv.normalize(img, None, 0, 255, NORM_MINMAX, CV_8U) (shared_modules/utils.py:94): scale, shift in f64,
+    applied as one f32 FMA, round half to even, saturate."""
+    smin, smax = float(img.min()), float(img.max())
+    scale = 255.0 * (1.0 / (smax - smin) if smax - smin > 2.220446049250313e-16 else 0.0)
+    shift = 0.0 - smin * scale
+    q = _fma32(img.astype(F32), np.full(1, scale, F32), np.full(1, shift, F32))
+    return np.clip(np.rint(q), 0, 255).astype(np.uint8)
+
+
 # ------------------------------------------------------------------------------- NMI
 def nmi(a: np.ndarray, b: np.ndarray) -> float:
     """sklearn.metrics.normalized_mutual_info_score(a, b) (arithmetic mean normaliser, natural log)

@@ -76,6 +76,9 @@ class CvBackend:
     def nmi(self, a, b):
         return float(self._nmi(a, b))
 
+    def normalize_u8(self, img):
+        return self.cv.normalize(img, None, 0, 255, self.cv.NORM_MINMAX, self.cv.CV_8U)
+
 
 class NpBackend:
     name = "numpy"
@@ -101,6 +104,9 @@ class NpBackend:
 
     def nmi(self, a, b):
         return cv_ops.nmi(a, b)
+
+    def normalize_u8(self, img):
+        return cv_ops.normalize_minmax_u8(img)
 
 
 # ------------------------------------------------------------------------------- tiles
@@ -274,3 +280,34 @@ def register(ref_img, mov_img, num_pyr_lvl=4, num_iterations=3, tile_size=1000, 
     if m_flow is None:
         raise UnboundLocalError("cannot access local variable 'm_flow' where it is not associated with a value")
     return m_flow
+
+
+# ------------------------------------------------------------------------------- pipeline dispatch
+def max_project(pages, be):
+    """read_and_max_project_pages (shared_modules/utils.py:75-95)."""
+    m = pages[0]
+    for p in pages[1:]:
+        m = np.maximum(m, p)
+    return be.normalize_u8(m)
+
+
+def register_cycles(dataset, ref_channel, be=None, **params):
+    """register_and_save_ofreg_imgs (__main__.py:320-437) on an in-memory dataset
+    {cycle: {channel: {z: page}}}; returns {(cycle, channel, z): image}."""
+    be = be or CvBackend()
+    T, ov = params.get("tile_size", 1000), params.get("overlap", 100)
+    out, ref_img = {}, None
+    for cyc_id, cyc in enumerate(dataset):
+        mip = max_project(list(dataset[cyc][ref_channel].values()), be)
+        if cyc_id == 0:
+            ref_img = mip
+            for ch, pages in dataset[cyc].items():
+                for z, page in pages.items():
+                    out[(cyc, ch, z)] = page
+            continue
+        flow = register(ref_img, mip, be=be, **params)
+        ref_img = warp(mip, flow, T, ov, be)
+        for ch, pages in dataset[cyc].items():
+            for z, page in pages.items():
+                out[(cyc, ch, z)] = warp(page, flow, T, ov, be)
+    return out

@@ -33,8 +33,8 @@ def test_argument_validation_without_gpu():
     assert lib.ma_dog_u8(None, 0, 0, 30, 30, None, 0, None, None) == -1
     # workspace sizing is pure host arithmetic
     S, Sp = 1200, 1216
-    assert lib.ma_farneback_workspace_bytes(5000, 5000, 1000, 100, 3) == 3 * 20 * S * Sp * 4
-    assert lib.ma_farneback_workspace_bytes(640, 512, 0, 0, 1) == 20 * 640 * 512 * 4
+    assert lib.ma_farneback_workspace_bytes(5000, 5000, 1000, 100, 3) == 3 * 22 * S * Sp * 4
+    assert lib.ma_farneback_workspace_bytes(640, 512, 0, 0, 1) == 22 * 640 * 512 * 4
     assert lib.ma_merge_workspace_bytes(2500, 3100, 1000) == 3 * 4 * 2 * 4
     assert lib.ma_nmi_workspace_bytes(10 ** 6, 10 ** 6) == 65536 * 4
     assert lib.ma_nmi_workspace_bytes(4 * 10 ** 8, 10 ** 6) == 64 * 65536 * 4
