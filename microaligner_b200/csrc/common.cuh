@@ -52,7 +52,12 @@ struct TileGeom {
     int ov;        // overlap
     int Sh, Sw;    // window size = core + 2*ov
     int ny, nx;    // tile grid
+    unsigned long long magic_h, magic_w;  // ceil(2^40 / Th), ceil(2^40 / Tw): exact n / T for n*T < 2^40
 };
+
+// n / Th and n / Tw without an integer division (n < 2^20, T < 2^20)
+__host__ __device__ __forceinline__ int div_th(const TileGeom& g, int n) { return (int)(((unsigned long long)(unsigned)n * g.magic_h) >> 40); }
+__host__ __device__ __forceinline__ int div_tw(const TileGeom& g, int n) { return (int)(((unsigned long long)(unsigned)n * g.magic_w) >> 40); }
 
 static inline TileGeom make_geom(int h, int w, int T, int ov) {
     TileGeom g;
@@ -63,6 +68,8 @@ static inline TileGeom make_geom(int h, int w, int T, int ov) {
     g.Sw = g.Tw + 2 * g.ov;
     g.ny = (h + g.Th - 1) / g.Th;
     g.nx = (w + g.Tw - 1) / g.Tw;
+    g.magic_h = ((1ull << 40) + g.Th - 1) / g.Th;
+    g.magic_w = ((1ull << 40) + g.Tw - 1) / g.Tw;
     return g;
 }
 

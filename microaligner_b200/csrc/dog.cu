@@ -16,11 +16,15 @@
 // Both global reductions stay on the device (ordered-key atomicMin/Max); nothing syncs with the host.
 #include <cmath>
 #include "common.cuh"
+#include "packed.cuh"
+#include "tma.cuh"
 
 namespace ma {
 
 struct DogTaps {
     float k5[41], k9[41];
+    float2 c5[21], c9[21];   // k[20 + j] duplicated {k, k}: taps of the symmetric column pass (packed f32x2)
+    float2 negzero2;         // {-0.f, -0.f}, see packed.cuh:mul2
 };
 
 static void make_dog_taps(DogTaps& t) {
@@ -35,7 +39,12 @@ static void make_dog_taps(DogTaps& t) {
         }
         sum = 1. / sum;
         for (int i = 0; i < 41; ++i) (which ? t.k9 : t.k5)[i] = (float)(k[i] * sum);
+        for (int j = 0; j <= 20; ++j) {
+            float v = (which ? t.k9 : t.k5)[20 + j];
+            (which ? t.c9 : t.c5)[j] = make_float2(v, v);
+        }
     }
+    t.negzero2 = make_float2(-0.0f, -0.0f);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -105,112 +114,189 @@ __device__ __forceinline__ void norm255_coeffs(const float* __restrict__ mm, flo
 }
 
 // ------------------------------------------------------------------------------------------------
-// row pass: 4 consecutive outputs per thread, both sigmas from one staged, normalised row segment
+// row pass: a block owns one 512-pixel segment and walks down DOG_HROWS rows.  Per row the raw pixels
+// (+20 REFLECT_101 halo) are normalised into shared memory; the loads of the NEXT row are issued
+// before the current row is convolved, so their latency hides behind the 328 FMAs per thread.
+// 4 consecutive outputs per thread, both sigmas from the same 44 staged inputs.
 // ------------------------------------------------------------------------------------------------
 constexpr int DOG_HT = 128;            // threads per row segment
 constexpr int DOG_HW = DOG_HT * 4;     // outputs per row segment
-constexpr int DOG_HROWS = 2;           // rows per block
+constexpr int DOG_HROWS = 16;          // rows per block
+constexpr int DOG_SEG = DOG_HW + 40;   // staged inputs per row
+constexpr int DOG_NLD = (DOG_SEG + DOG_HT - 1) / DOG_HT;
 
 template <typename T>
-__global__ void __launch_bounds__(DOG_HT* DOG_HROWS) dog_row_kernel(const T* __restrict__ src, size_t pitch, int h, int w,
-                                                                     const float* __restrict__ src_mm,
-                                                                     float* __restrict__ A5, float* __restrict__ A9, int wp,
-                                                                     const __grid_constant__ DogTaps taps, int ybeg, int yend) {
-    __shared__ __align__(16) float seg[DOG_HROWS][DOG_HW + 40];
-    int ry = threadIdx.y, y = ybeg + blockIdx.y * DOG_HROWS + ry;
-    int xb = blockIdx.x * DOG_HW;
+__global__ void __launch_bounds__(DOG_HT) dog_row_kernel(const T* __restrict__ src, size_t pitch, int h, int w,
+                                                         const float* __restrict__ src_mm,
+                                                         float* __restrict__ A5, float* __restrict__ A9, int wp,
+                                                         const __grid_constant__ DogTaps taps, int ybeg, int yend) {
+    __shared__ __align__(16) float seg[2][DOG_SEG];
+    const int xb = blockIdx.x * DOG_HW;
+    const int y_first = ybeg + blockIdx.y * DOG_HROWS;
     float a, b;
     norm01_coeffs(src_mm, a, b);
-    h = yend;  // rows [ybeg, yend) of the image are filtered
-    if (y < h) {
+    int col[DOG_NLD];
+#pragma unroll
+    for (int q = 0; q < DOG_NLD; ++q) {
+        int i = threadIdx.x + q * DOG_HT, xx = xb - 20 + i;
+        col[q] = (i < DOG_SEG && xx < w + 20) ? reflect101(xx, w) : -1;
+    }
+    T raw[DOG_NLD];
+    auto fetch = [&](int y) {
         const T* row = (const T*)((const char*)src + (size_t)y * pitch);
-        for (int i = threadIdx.x; i < DOG_HW + 40; i += DOG_HT) {
-            int xx = xb - 20 + i;
-            float v = 0.0f;
-            if (xx < w + 20) v = __fmaf_rn((float)__ldg(row + reflect101(xx, w)), a, b);
-            seg[ry][i] = v;
+#pragma unroll
+        for (int q = 0; q < DOG_NLD; ++q) raw[q] = col[q] >= 0 ? __ldg(row + col[q]) : (T)0;
+    };
+    if (y_first < yend) fetch(y_first);
+    const int x0 = xb + threadIdx.x * 4;
+    const bool fused = x0 < (w & ~3);  // vector body of OpenCV's row filter; the last w & 3 columns are scalar code
+#pragma unroll 1
+    for (int r = 0; r < DOG_HROWS; ++r) {
+        const int y = y_first + r;
+        if (y >= yend) break;
+        float* sg = seg[r & 1];
+#pragma unroll
+        for (int q = 0; q < DOG_NLD; ++q) {
+            int i = threadIdx.x + q * DOG_HT;
+            if (i < DOG_SEG) sg[i] = col[q] >= 0 ? __fmaf_rn((float)raw[q], a, b) : 0.0f;
         }
-    }
-    __syncthreads();
-    int x0 = xb + threadIdx.x * 4;
-    if (y >= h || x0 >= w) return;
-    float in[44];
+        __syncthreads();
+        if (y + 1 < yend && r + 1 < DOG_HROWS) fetch(y + 1);
+        if (x0 >= w) continue;
+        float in[44];
 #pragma unroll
-    for (int q = 0; q < 11; ++q) {
-        float4 v = *reinterpret_cast<const float4*>(&seg[ry][threadIdx.x * 4 + q * 4]);
-        in[4 * q] = v.x; in[4 * q + 1] = v.y; in[4 * q + 2] = v.z; in[4 * q + 3] = v.w;
-    }
-    float s5[4] = {0.f, 0.f, 0.f, 0.f}, s9[4] = {0.f, 0.f, 0.f, 0.f};
-    if (x0 < (w & ~3)) {  // vector body of OpenCV's row filter: fused
+        for (int q = 0; q < 11; ++q) {
+            float4 v = *reinterpret_cast<const float4*>(&sg[threadIdx.x * 4 + q * 4]);
+            in[4 * q] = v.x; in[4 * q + 1] = v.y; in[4 * q + 2] = v.z; in[4 * q + 3] = v.w;
+        }
+        float s5[4] = {0.f, 0.f, 0.f, 0.f}, s9[4] = {0.f, 0.f, 0.f, 0.f};
+        if (fused) {
 #pragma unroll
-        for (int j = 0; j < 41; ++j)
+            for (int j = 0; j < 41; ++j)
 #pragma unroll
-            for (int o = 0; o < 4; ++o) {
-                s5[o] = __fmaf_rn(in[o + j], taps.k5[j], s5[o]);
-                s9[o] = __fmaf_rn(in[o + j], taps.k9[j], s9[o]);
-            }
-    } else {  // scalar tail: multiply and add rounded separately
+                for (int o = 0; o < 4; ++o) {
+                    s5[o] = __fmaf_rn(in[o + j], taps.k5[j], s5[o]);
+                    s9[o] = __fmaf_rn(in[o + j], taps.k9[j], s9[o]);
+                }
+        } else {  // scalar tail: multiply and add rounded separately
 #pragma unroll
-        for (int j = 0; j < 41; ++j)
+            for (int j = 0; j < 41; ++j)
 #pragma unroll
-            for (int o = 0; o < 4; ++o) {
-                s5[o] = __fadd_rn(s5[o], __fmul_rn(in[o + j], taps.k5[j]));
-                s9[o] = __fadd_rn(s9[o], __fmul_rn(in[o + j], taps.k9[j]));
-            }
-    }
-    size_t o = (size_t)y * wp + x0;
-    if (x0 + 3 < w) {
-        *reinterpret_cast<float4*>(A5 + o) = make_float4(s5[0], s5[1], s5[2], s5[3]);
-        *reinterpret_cast<float4*>(A9 + o) = make_float4(s9[0], s9[1], s9[2], s9[3]);
-    } else {
-        for (int q = 0; q < 4 && x0 + q < w; ++q) { A5[o + q] = s5[q]; A9[o + q] = s9[q]; }
+                for (int o = 0; o < 4; ++o) {
+                    s5[o] = __fadd_rn(s5[o], __fmul_rn(in[o + j], taps.k5[j]));
+                    s9[o] = __fadd_rn(s9[o], __fmul_rn(in[o + j], taps.k9[j]));
+                }
+        }
+        const size_t o = (size_t)y * wp + x0;
+        if (x0 + 3 < w) {
+            *reinterpret_cast<float4*>(A5 + o) = make_float4(s5[0], s5[1], s5[2], s5[3]);
+            *reinterpret_cast<float4*>(A9 + o) = make_float4(s9[0], s9[1], s9[2], s9[3]);
+        } else {
+            for (int q = 0; q < 4 && x0 + q < w; ++q) { A5[o + q] = s5[q]; A9[o + q] = s9[q]; }
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // column pass: lane <-> column, 8 consecutive rows per thread; d = blur9 - blur5; min/max of d
 // ------------------------------------------------------------------------------------------------
-constexpr int DOG_VR = 8;
+
+// ------------------------------------------------------------------------------------------------
+// column pass: CTA = 64 columns x 64 rows.  The two row-filtered planes arrive as two TMA boxes
+// (64 x 104 floats each, zero fill outside the plane); REFLECT_101 rows are mirrored in shared memory.
+// A thread owns the column pair (2*lane, 2*lane+1) as one packed f32x2 value and 8 consecutive rows,
+// with two 8-deep sliding windows in registers (2 LDS.64 per 8 x (FADD2, FFMA2)).
+// d = blur9 - blur5 goes to D; min/max of d to the ordered-key atomics.
+// ------------------------------------------------------------------------------------------------
+constexpr int DC_OUT = 64, DC_ROWS = DC_OUT + 40, DC_ROWU = 32;
 
 template <bool FUSED>
-__device__ __forceinline__ void col_conv8(const float* __restrict__ P, int wp, int h, int x, int y0, const float* k, float (&s)[DOG_VR]) {
-    float in[DOG_VR + 40];
+__device__ __forceinline__ void col_conv8x2(const u64* __restrict__ centre, const float2* __restrict__ k2, u64 nz, u64 (&acc)[8]) {
+    u64 wp[8], wm[8];
+    const u64 k0 = *reinterpret_cast<const u64*>(&k2[0]);
 #pragma unroll
-    for (int q = 0; q < DOG_VR + 40; ++q) in[q] = __ldg(P + (size_t)reflect101(min(y0 - 20 + q, h + 19), h) * wp + x);
+    for (int j = 0; j < 8; ++j) {
+        u64 c = centre[j * DC_ROWU];
+        wp[j] = c;
+        wm[j] = c;
+        acc[j] = mul2(c, k0, nz);
+    }
+    // step i = 1..20 (fully unrolled: static register rotation, see farneback.cu:conv8x2)
 #pragma unroll
-    for (int o = 0; o < DOG_VR; ++o) s[o] = __fmul_rn(in[o + 20], k[20]);
+    for (int i = 1; i <= 20; ++i) {
+        const int s = (i - 1) & 7;
+        wp[s] = centre[(7 + i) * DC_ROWU];
+        wm[(63 - s) & 7] = centre[-i * DC_ROWU];
+        const u64 kk = *reinterpret_cast<const u64*>(&k2[i]);
 #pragma unroll
-    for (int j = 1; j <= 20; ++j)
-#pragma unroll
-        for (int o = 0; o < DOG_VR; ++o) {
-            float pr = __fadd_rn(in[o + 20 + j], in[o + 20 - j]);
-            s[o] = FUSED ? __fmaf_rn(pr, k[20 + j], s[o]) : __fadd_rn(s[o], __fmul_rn(pr, k[20 + j]));
+        for (int j = 0; j < 8; ++j) {
+            u64 pr = add2(wp[(j + s + 1) & 7], wm[(j + 63 - s) & 7]);
+            acc[j] = FUSED ? fma2(pr, kk, acc[j]) : add2(acc[j], mul2(pr, kk, nz));
         }
+    }
 }
 
-__global__ void __launch_bounds__(256) dog_col_kernel(const float* __restrict__ A5, const float* __restrict__ A9, int wp, int h, int w,
+__global__ void __launch_bounds__(256) dog_col_kernel(const __grid_constant__ CUtensorMap mapA, int wp, int h, int w,
                                                       float* __restrict__ D, unsigned* keys_out,
                                                       const __grid_constant__ DogTaps taps, int ybeg, int yend) {
-    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int x = blockIdx.x * 32 + lane;
-    int y0 = ybeg + (blockIdx.y * 8 + warp) * DOG_VR;
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t bar;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x0 = blockIdx.x * 64, y0 = ybeg + blockIdx.y * DC_OUT;
+    const int v_first = y0 - 20;
+    float* buf5 = smem;
+    float* buf9 = smem + DC_ROWS * 64;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, 2 * DC_ROWS * 64 * sizeof(float));
+        tma_load_3d(buf5, &mapA, x0, v_first, 0, &bar);
+        tma_load_3d(buf9, &mapA, x0, v_first, 1, &bar);
+    }
+    mbar_wait(&bar, 0);
+    if (v_first < 0 || v_first + DC_ROWS > h) {  // CTA-uniform: mirror the rows outside the image
+        for (int p = threadIdx.x; p < DC_ROWS * 64; p += 256) {
+            int r = p >> 6, c = p & 63, v = v_first + r;
+            if (v < 0 || v >= h) {
+                int rr = min(max(reflect101(min(v, 2 * h - 2), h) - v_first, 0), DC_ROWS - 1);
+                buf5[p] = buf5[rr * 64 + c];
+                buf9[p] = buf9[rr * 64 + c];
+            }
+        }
+        __syncthreads();
+    }
     float lo = INFINITY, hi = -INFINITY;
-    if (x < w && y0 < yend) {
-        float s5[DOG_VR], s9[DOG_VR];
+    const int x = x0 + 2 * lane, o0 = warp * 8;
+    if (x < w && y0 + o0 < yend) {
+        const u64 nz = *reinterpret_cast<const u64*>(&taps.negzero2);
+        u64 s5[8], s9[8];
+        const u64* c5 = reinterpret_cast<const u64*>(buf5) + (o0 + 20) * DC_ROWU + lane;
+        const u64* c9 = reinterpret_cast<const u64*>(buf9) + (o0 + 20) * DC_ROWU + lane;
         if (x < (w & ~7)) {
-            col_conv8<true>(A5, wp, h, x, y0, taps.k5, s5);
-            col_conv8<true>(A9, wp, h, x, y0, taps.k9, s9);
+            col_conv8x2<true>(c5, taps.c5, nz, s5);
+            col_conv8x2<true>(c9, taps.c9, nz, s9);
         } else {
-            col_conv8<false>(A5, wp, h, x, y0, taps.k5, s5);
-            col_conv8<false>(A9, wp, h, x, y0, taps.k9, s9);
+            col_conv8x2<false>(c5, taps.c5, nz, s5);
+            col_conv8x2<false>(c9, taps.c9, nz, s9);
         }
 #pragma unroll
-        for (int o = 0; o < DOG_VR; ++o) {
-            if (y0 + o < yend) {
-                float d = __fsub_rn(s9[o], s5[o]);
-                D[(size_t)(y0 + o) * wp + x] = d;
-                lo = fminf(lo, d);
-                hi = fmaxf(hi, d);
+        for (int j = 0; j < 8; ++j) {
+            const int y = y0 + o0 + j;
+            if (y < yend) {
+                float2 d = unpack2(sub2(s9[j], s5[j]));
+                float* out = D + (size_t)y * wp + x;
+                if (x + 1 < w) {
+                    *reinterpret_cast<float2*>(out) = d;
+                    lo = fminf(lo, fminf(d.x, d.y));
+                    hi = fmaxf(hi, fmaxf(d.x, d.y));
+                } else {
+                    out[0] = d.x;
+                    lo = fminf(lo, d.x);
+                    hi = fmaxf(hi, d.x);
+                }
             }
         }
     }
@@ -323,12 +409,23 @@ extern "C" int ma_dog_diff_rows(const void* src, size_t src_pitch, int dtype, in
     if (row_begin < row_end) {
         int ra = std::max(row_begin - 20, 0), rb = std::min(row_end + 20, h);
         double px = (double)(row_end - row_begin) * w;
-        dim3 rg(ceil_div(w, DOG_HW), ceil_div(rb - ra, DOG_HROWS)), rbk(DOG_HT, DOG_HROWS);
+        dim3 rg(ceil_div(w, DOG_HW), ceil_div(rb - ra, DOG_HROWS)), rbk(DOG_HT);
         { KernelScope ks(K_DOG_ROW, s, px);
         if (dtype == MA_U8) dog_row_kernel<uint8_t><<<rg, rbk, 0, s>>>((const uint8_t*)src, src_pitch, h, w, src_minmax, A5, A9, wp, taps, ra, rb);
         else dog_row_kernel<uint16_t><<<rg, rbk, 0, s>>>((const uint16_t*)src, src_pitch, h, w, src_minmax, A5, A9, wp, taps, ra, rb); }
         { KernelScope ks(K_DOG_COL, s, px);
-        dog_col_kernel<<<dim3(ceil_div(w, 32), ceil_div(row_end - row_begin, 8 * DOG_VR)), 256, 0, s>>>(A5, A9, wp, h, w, diff, keys, taps, row_begin, row_end); }
+        CUtensorMap mapA;
+        if (!make_plane_map(&mapA, A5, (uint64_t)w, (uint64_t)h, 2, (uint64_t)wp * 4, (uint64_t)h * wp * 4, 64, DC_ROWS)) {
+            set_error("ma_dog_diff_rows: cuTensorMapEncodeTiled failed");
+            return MA_ERR_CUDA;
+        }
+        static bool attr_set = false;
+        if (!attr_set) {
+            MA_CUDA_CHECK(cudaFuncSetAttribute(dog_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * DC_ROWS * 64 * 4));
+            attr_set = true;
+        }
+        dog_col_kernel<<<dim3(ceil_div(w, 64), ceil_div(row_end - row_begin, DC_OUT)), 256, 2 * DC_ROWS * 64 * 4, s>>>(
+            mapA, wp, h, w, diff, keys, taps, row_begin, row_end); }
     }
     { KernelScope ks(K_SMALL, s); keys_to_float_kernel<<<1, 1, 0, s>>>(keys, diff_minmax); }
     MA_LAUNCH_CHECK("dog diff kernels");

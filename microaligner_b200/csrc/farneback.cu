@@ -24,6 +24,7 @@
 #include <cmath>
 #include <vector>
 #include "common.cuh"
+#include "packed.cuh"
 #include "tma.cuh"
 
 namespace ma {
@@ -262,32 +263,6 @@ __device__ __forceinline__ void update_matrices_px(const float* __restrict__ R0,
 // makes the separately-rounded add/mul/add sequence as cheap as a fused scalar FMA formulation.
 // With the loop unrolled by 8 every register index is static.
 // ------------------------------------------------------------------------------------------------
-typedef unsigned long long u64;
-__device__ __forceinline__ u64 add2(u64 a, u64 b) {
-    u64 r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-// a*b rounded once.  ptxas contracts a mul.rn.f32x2 feeding an add.rn.f32x2 into one FFMA2 (observed
-// in SASS, also with a literal -0 addend), which would break parity with OpenCV's unfused arithmetic.
-// The product is therefore an explicit fma with a -0 addend that arrives as a *runtime* value
-// (FbConsts::negzero2): x*k + (-0) == x*k exactly, and the following add cannot be merged into it.
-__device__ __forceinline__ u64 mul2(u64 a, u64 b, u64 negzero) {
-    u64 r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(negzero));
-    return r;
-}
-__device__ __forceinline__ u64 pack2(float x, float y) {
-    u64 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
-    return r;
-}
-__device__ __forceinline__ float2 unpack2(u64 v) {
-    float2 r;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
-    return r;
-}
-
 constexpr int kRowF = 64;            // floats per shared-memory row (one TMA box row)
 constexpr int kRowU = kRowF / 2;     // packed pairs per row
 

@@ -43,20 +43,29 @@ __global__ void __launch_bounds__(256) warp_tiles_kernel(const T* __restrict__ i
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = ybeg + blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= g.w || y >= yend) return;
-    int ti = y / g.Th, tj = x / g.Tw;
+    int ti = div_th(g, y), tj = div_tw(g, x);
     int ty = g.ov + (y - ti * g.Th), tx = g.ov + (x - tj * g.Tw);  // tile-local pixel
     int oy = ti * g.Th - g.ov, ox = tj * g.Tw - g.ov;              // window origin in the image
     float2 f = __ldg(&flow[(size_t)y * g.w + x]);
     Taps t = make_taps(__fsub_rn((float)tx, f.x), __fsub_rn((float)ty, f.y));
-
-    auto tap = [&](int yy, int xx) -> T {
-        // inside the S x S window and inside the image (window is zero padded beyond it)
-        int gy = oy + yy, gx = ox + xx;
-        bool ok = (unsigned)xx < (unsigned)g.Sw && (unsigned)yy < (unsigned)g.Sh &&
-                  (unsigned)gx < (unsigned)g.w && (unsigned)gy < (unsigned)g.h;
-        return ok ? __ldg((const T*)((const char*)img + (size_t)gy * img_pitch) + gx) : (T)0;
-    };
-    T v00 = tap(t.iy, t.ix), v01 = tap(t.iy, t.ix + 1), v10 = tap(t.iy + 1, t.ix), v11 = tap(t.iy + 1, t.ix + 1);
+    T v00, v01, v10, v11;
+    const int gy0 = oy + t.iy, gx0 = ox + t.ix;
+    if ((unsigned)t.ix < (unsigned)(g.Sw - 1) && (unsigned)t.iy < (unsigned)(g.Sh - 1) &&
+        (unsigned)gx0 < (unsigned)(g.w - 1) && (unsigned)gy0 < (unsigned)(g.h - 1)) {
+        // common case: all four taps inside the tile window and the image
+        const T* p0 = (const T*)((const char*)img + (size_t)gy0 * img_pitch) + gx0;
+        const T* p1 = (const T*)((const char*)p0 + img_pitch);
+        v00 = __ldg(p0); v01 = __ldg(p0 + 1); v10 = __ldg(p1); v11 = __ldg(p1 + 1);
+    } else {
+        auto tap = [&](int yy, int xx) -> T {
+            // inside the S x S window and inside the image (window is zero padded beyond it)
+            int gy = oy + yy, gx = ox + xx;
+            bool ok = (unsigned)xx < (unsigned)g.Sw && (unsigned)yy < (unsigned)g.Sh &&
+                      (unsigned)gx < (unsigned)g.w && (unsigned)gy < (unsigned)g.h;
+            return ok ? __ldg((const T*)((const char*)img + (size_t)gy * img_pitch) + gx) : (T)0;
+        };
+        v00 = tap(t.iy, t.ix); v01 = tap(t.iy, t.ix + 1); v10 = tap(t.iy + 1, t.ix); v11 = tap(t.iy + 1, t.ix + 1);
+    }
     T r;
     if (sizeof(T) == 1) {
         int w00 = (32 - t.ay) * (32 - t.ax) * 32, w01 = (32 - t.ay) * t.ax * 32;
@@ -118,7 +127,7 @@ __global__ void __launch_bounds__(256) merge_tiles_kernel(const float2* __restri
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = ybeg + blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= g.w || y >= yend) return;
-    int ti = y / g.Th, tj = x / g.Tw;
+    int ti = div_th(g, y), tj = div_tw(g, x);
     int tile = ti * g.nx + tj;
     size_t idx = (size_t)y * g.w + x;
     float max1 = key2f(keys[2 * tile]), max2 = key2f(keys[2 * tile + 1]);
