@@ -4,6 +4,7 @@ torch is used for device memory, streams and (in parallel.py) the process group 
 arithmetic happens in libmicroaligner_b200.so.  Images are 2-D uint8/uint16 tensors (uint16 is
 carried as torch.uint16), flows are (H, W, 2) float32 tensors, all C-contiguous on one device."""
 import ctypes
+import weakref
 from typing import Optional, Sequence
 
 import numpy as np
@@ -42,24 +43,41 @@ def _bytes(n: int, device) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------- host <-> device
+_MIRRORS = {}   # id(host array) -> (weakref to the array, device tensor it mirrors)
+
+
 def to_device(arr, device=None) -> torch.Tensor:
-    """numpy (uint8/uint16/float32) or torch tensor -> contiguous CUDA tensor."""
+    """numpy (uint8/uint16/float32) or torch tensor -> contiguous CUDA tensor.  A read-only array handed out
+    by to_host(mirror=True) is recognised by identity and mapped back to its device copy without a transfer."""
     if isinstance(arr, torch.Tensor):
         t = arr if arr.is_cuda else arr.to(device or "cuda")
         return t.contiguous()
+    m = _MIRRORS.get(id(arr))
+    if m is not None and m[0]() is arr and not arr.flags.writeable:
+        return m[1]
     a = np.ascontiguousarray(arr)
     if a.dtype not in (np.uint8, np.uint16, np.float32):
         raise TypeError(f"unsupported dtype {a.dtype}; expected uint8, uint16 or float32")
     return torch.from_numpy(a).to(device or "cuda", non_blocking=False)
 
 
-def to_host(t: torch.Tensor) -> np.ndarray:
-    """Device tensor -> numpy array backed by page-locked memory (torch's caching host allocator
-    recycles the pinned block once the array is garbage collected), one DMA transfer."""
+def to_host(t: torch.Tensor, mirror: bool = False) -> np.ndarray:
+    """Device tensor -> numpy array backed by page-locked memory (torch's caching host allocator recycles
+    the pinned block once the array is garbage collected), one DMA transfer.
+
+    mirror=True marks the array READ-ONLY and remembers the device tensor it was copied from for as long as
+    the array lives: passing that very array back (e.g. register() -> Warper.flow) then costs no upload.
+    Read-only is what makes this safe -- the host copy cannot silently diverge from the device copy; call
+    .copy() to get a writeable, un-mirrored array."""
     host = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True)
     host.copy_(t, non_blocking=True)
     torch.cuda.current_stream().synchronize()
-    return host.numpy()
+    arr = host.numpy()
+    if mirror:
+        arr.flags.writeable = False
+        key = id(arr)
+        _MIRRORS[key] = (weakref.ref(arr, lambda _r, key=key: _MIRRORS.pop(key, None)), t)
+    return arr
 
 
 def pinned_like(arr: np.ndarray) -> np.ndarray:

@@ -34,6 +34,9 @@ class OptFlowRegistrator:
         self._warper = Warper()
         self._tile_flow_calc = TileFlowCalc()
         self.decisions: List[dict] = []  # per level: factor, mi_after, mi_before, better (diagnostic)
+        # numpy results are read-only and stay mirrored on the device (ops.to_host): handing the flow to
+        # Warper.flow then needs no upload.  Set False for a plain writeable array, as the reference returns.
+        self.mirror_flow = True
 
     @property
     def ref_img(self):
@@ -143,4 +146,4 @@ class OptFlowRegistrator:
                      self.use_dog, comm=parallel.get())
         m_flow = eng.register(ref, mov)     # the coarse-to-fine loop, sharded over the ranks of parallel.get()
         self.decisions = eng.decisions
-        return ops.to_host(m_flow) if host_result else m_flow
+        return ops.to_host(m_flow, mirror=self.mirror_flow) if host_result else m_flow

@@ -96,3 +96,38 @@ def test_errors(cuda):
     reg.mov_img = np.zeros((150, 150), np.uint8)
     with pytest.raises(UnboundLocalError):
         reg.register()
+
+
+def test_mirrored_flow_is_read_only_and_reused(cuda):
+    from microaligner_b200 import OptFlowRegistrator, Warper, ops
+    ref, mov = synth_pair(500, 420, 4, np.uint16)
+    reg = OptFlowRegistrator()
+    reg.num_pyr_lvl, reg.tile_size, reg.overlap = 1, 200, 30
+    reg.ref_img, reg.mov_img = ref, mov
+    with contextlib.redirect_stdout(io.StringIO()):
+        flow = reg.register()
+    assert not flow.flags.writeable
+    with pytest.raises(ValueError):
+        flow[0, 0, 0] = 1.0
+    dev = ops.to_device(flow)
+    assert dev is ops.to_device(flow)                      # recognised by identity: no new upload
+    w = Warper()
+    w.tile_size, w.overlap = 200, 30
+    w.image, w.flow = mov, flow
+    a = w.warp()
+    edited = flow.copy()                                    # a copy is writeable and not mirrored
+    edited[...] = 0
+    assert ops.to_device(edited) is not dev
+    w.image, w.flow = mov, edited
+    b = w.warp()
+    assert np.array_equal(b, mov) and not np.array_equal(a, b)
+    key = id(flow)
+    del flow, dev
+    import gc
+    gc.collect()
+    assert key not in ops._MIRRORS                          # the device copy is released with the host array
+    reg.mirror_flow = False
+    reg.ref_img, reg.mov_img = ref, mov
+    with contextlib.redirect_stdout(io.StringIO()):
+        plain = reg.register()
+    assert plain.flags.writeable
