@@ -20,8 +20,8 @@ Range = Tuple[int, int]
 
 
 def _clip(a: int, b: int, h: int) -> Range:
-    a, b = max(a, 0), min(b, h)
-    return (a, max(a, b))
+    a = min(max(a, 0), h)
+    return (a, min(max(b, a), h))
 
 
 def _union(a: Range, b: Range) -> Range:

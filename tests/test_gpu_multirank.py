@@ -59,7 +59,7 @@ def _free_port():
 
 
 @pytest.mark.parametrize("case_id", range(len(CASES)))
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [2, 3, 5])
 def test_sharded_equals_single(cuda, tmp_path, case_id, world):
     shape, dtype, kw = CASES[case_id]
     ref, mov = synth_pair(shape[0], shape[1], 7, dtype)
