@@ -191,6 +191,9 @@ def run_b200(args):
     for k, v in PARAMS.items():
         setattr(reg, k, v)
     wrp.tile_size, wrp.overlap = PARAMS["tile_size"], PARAMS["overlap"]
+    # N > 1: the flow stays sharded on the GPUs that computed it (each band is what that rank's warp reads);
+    # the final NVLink gather is that of the warped image
+    reg.gather_flow = False
 
     def step_device():
         reg.ref_img, reg.mov_img = ref_d, mov_d
@@ -210,7 +213,9 @@ def run_b200(args):
         comm.broadcast(r, 0)
         comm.broadcast(m, 0)
         reg.ref_img, reg.mov_img = r, m
+        reg.gather_flow = True          # the host wants the whole flow on rank 0
         flow = reg.register()
+        reg.gather_flow = False
         wrp.image, wrp.flow = m, flow
         out = wrp.warp()
         if rank == 0:
@@ -249,6 +254,13 @@ def run_b200(args):
         _lib.lib.ma_profile_enable(0)
         launches = _lib.lib.ma_launch_count() - launches0
         prof = _lib.profile_summary()
+        if args.trace:
+            from microaligner_b200.engine import Engine
+            Engine.trace = True
+            Engine.times.clear()
+            step_device()
+            Engine.trace = False
+            sys.stderr.write(f"[trace rank {rank}] " + json.dumps({k: round(v * 1e3, 2) for k, v in Engine.times.items()}) + "\n")
         # end-to-end through the numpy API (page-locked host arrays)
         for _ in range(max(3, args.warmup)):
             step_host()
@@ -334,6 +346,7 @@ def main():
     ap.add_argument("--size", type=int, default=20000)
     ap.add_argument("--cpu-sample", type=int, default=4000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--trace", action="store_true", help="extra untimed step with per-phase synchronised wall times (stderr)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

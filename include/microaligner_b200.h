@@ -45,6 +45,10 @@ const char* ma_last_error(void);
 int ma_pyrdown(const void* src, size_t src_pitch, int h, int w, int dtype,
                void* dst, size_t dst_pitch, void* stream);
 
+/* same, restricted to destination rows [row_begin, row_end) */
+int ma_pyrdown_rows(const void* src, size_t src_pitch, int h, int w, int dtype,
+                    void* dst, size_t dst_pitch, int row_begin, int row_end, void* stream);
+
 /* ---- flow up-sampling: cv.pyrUp(flow*scale, dstsize) (optflow_registrator.py:140,150,164,169,212)
  * src (h,w,2) -> dst (dh,dw,2), dh in {2h-1,2h}, dw in {2w-1,2w}; `scale` is the reference's
  * pre-multiplication of the flow (1, 2 or 4). */

@@ -28,6 +28,7 @@ PROTOTYPES = {
     "ma_version": (c_int, []),
     "ma_last_error": (c_char_p, []),
     "ma_pyrdown": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "ma_pyrdown_rows": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "ma_pyrup_flow": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_float, c_void_p]),
     "ma_warp_tiles": (c_int, [c_void_p, c_size_t, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "ma_warp_tiles_rows": (c_int, [c_void_p, c_size_t, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_int, c_int, c_void_p]),

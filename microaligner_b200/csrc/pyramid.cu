@@ -13,9 +13,9 @@ namespace ma {
 
 template <typename T>
 __global__ void __launch_bounds__(256) pyrdown_kernel(const T* __restrict__ src, size_t sp, int h, int w,
-                                                      T* __restrict__ dst, size_t dp, int oh, int ow) {
+                                                      T* __restrict__ dst, size_t dp, int oh, int ow, int ybeg) {
     int ox = blockIdx.x * blockDim.x + threadIdx.x;
-    int oy = blockIdx.y * blockDim.y + threadIdx.y;
+    int oy = ybeg + blockIdx.y * blockDim.y + threadIdx.y;
     if (ox >= ow || oy >= oh) return;
     int xs[5], acc = 0;
 #pragma unroll
@@ -74,21 +74,28 @@ __global__ void __launch_bounds__(256) pyrup_flow_kernel(const float2* __restric
 
 using namespace ma;
 
-extern "C" int ma_pyrdown(const void* src, size_t src_pitch, int h, int w, int dtype,
-                          void* dst, size_t dst_pitch, void* stream) {
+extern "C" int ma_pyrdown_rows(const void* src, size_t src_pitch, int h, int w, int dtype,
+                               void* dst, size_t dst_pitch, int row_begin, int row_end, void* stream) {
     if (!src || !dst || h < 3 || w < 3) return invalid("ma_pyrdown: bad argument (need h,w >= 3)");
     int oh = (h + 1) / 2, ow = (w + 1) / 2;
-    dim3 block(32, 8), grid(ceil_div(ow, 32), ceil_div(oh, 8));
+    if (row_begin < 0 || row_end > oh || row_begin > row_end) return invalid("ma_pyrdown: bad row range");
+    if (row_begin == row_end) return MA_OK;
+    dim3 block(32, 8), grid(ceil_div(ow, 32), ceil_div(row_end - row_begin, 8));
     cudaStream_t s = (cudaStream_t)stream;
-    KernelScope ks(K_PYRDOWN, s, (double)h * w);
+    KernelScope ks(K_PYRDOWN, s, 4.0 * (row_end - row_begin) * ow);
     if (dtype == MA_U8)
-        pyrdown_kernel<uint8_t><<<grid, block, 0, s>>>((const uint8_t*)src, src_pitch, h, w, (uint8_t*)dst, dst_pitch, oh, ow);
+        pyrdown_kernel<uint8_t><<<grid, block, 0, s>>>((const uint8_t*)src, src_pitch, h, w, (uint8_t*)dst, dst_pitch, row_end, ow, row_begin);
     else if (dtype == MA_U16)
-        pyrdown_kernel<uint16_t><<<grid, block, 0, s>>>((const uint16_t*)src, src_pitch, h, w, (uint16_t*)dst, dst_pitch, oh, ow);
+        pyrdown_kernel<uint16_t><<<grid, block, 0, s>>>((const uint16_t*)src, src_pitch, h, w, (uint16_t*)dst, dst_pitch, row_end, ow, row_begin);
     else
         return invalid("ma_pyrdown: dtype must be MA_U8 or MA_U16");
     MA_LAUNCH_CHECK("pyrdown_kernel");
     return MA_OK;
+}
+
+extern "C" int ma_pyrdown(const void* src, size_t src_pitch, int h, int w, int dtype,
+                          void* dst, size_t dst_pitch, void* stream) {
+    return ma_pyrdown_rows(src, src_pitch, h, w, dtype, dst, dst_pitch, 0, (h + 1) / 2, stream);
 }
 
 extern "C" int ma_pyrup_flow_rows(const float* src, int h, int w, float* dst, int dh, int dw, float scale,

@@ -8,6 +8,9 @@ reads) is fetched from the owner with point-to-point row exchanges.  Global scal
 the per-chunk NMI scores -- are all-reduced, so every rank takes the same Better/Worse decision.
 Levels the reference computes untiled (max(shape)/tile_size < 2) are tiny and run replicated.
 With one rank every exchange is a no-op and the code below is simply the single-GPU path."""
+import contextlib
+import time
+from collections import defaultdict
 from math import log2
 from typing import Callable, List, Optional, Sequence, Tuple
 
@@ -39,9 +42,12 @@ class LevelLayout:
         if self.sharded:
             self.tile_rows = comm.tile_row_bands(self.ny)
             self.bands = [_clip(a * T, b * T, h) for a, b in self.tile_rows]
+            # Farneback (4/5 of the work) is balanced at TILE granularity, independently of the row bands
+            self.fb_tiles = parallel.split_even(self.ny * self.nx, comm.world)
         else:
             self.tile_rows = [(0, self.ny)] * comm.world
             self.bands = [(0, h)] * comm.world
+            self.fb_tiles = [(0, self.ny * self.nx)] * comm.world
         self.rank = comm.rank
         self.world = comm.world
 
@@ -52,6 +58,20 @@ class LevelLayout:
     @property
     def band(self) -> Range:
         return self.bands[self.rank]
+
+    def fb_window_rows(self, halo: int = 0) -> List[Range]:
+        """Image rows covered by the tile windows of every rank's Farneback tiles (+ halo)."""
+        out = []
+        for t0, t1 in self.fb_tiles:
+            if t1 <= t0:
+                out.append((0, 0))
+            else:
+                i0, i1 = t0 // self.nx, (t1 - 1) // self.nx
+                out.append(_clip(i0 * self.T - self.ov - halo, (i1 + 1) * self.T + self.ov + halo, self.h))
+        return out
+
+    def fb_rects(self):
+        return [parallel.tile_range_rects(t, self.nx, self.T, self.h, self.w) for t in self.fb_tiles]
 
 
 class Engine:
@@ -64,10 +84,27 @@ class Engine:
         self.win = self.ov - (1 - self.ov % 2)         # optflow_registrator.py:91
         self._log = log
         self.decisions: List[dict] = []
+        self.gather_flow = True      # False: with several ranks the returned flow is valid on this rank's band only
+        self.flow_layout = None
 
     def log(self, *a):
         if self.comm.rank == 0:
             (self._log or print)(*a)
+
+    # optional phase tracing (Engine.trace = True): device-synchronised wall time per phase, summed in Engine.times
+    trace = False
+    times = defaultdict(float)
+
+    @contextlib.contextmanager
+    def phase(self, name):
+        if not Engine.trace:
+            yield
+            return
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        yield
+        torch.cuda.synchronize()
+        Engine.times[name] += time.perf_counter() - t
 
     # ------------------------------------------------------------------ building blocks
     def pyramid(self, arr: torch.Tensor):
@@ -81,7 +118,15 @@ class Engine:
             factor = 2 ** (lvl + 1)
             if arr.shape[0] / factor < 100 or arr.shape[1] / factor < 100:
                 break
-            cur = ops.pyr_down(cur)
+            if self.comm.world > 1 and cur.shape[0] >= 64 * self.comm.world:
+                # every rank reduces its slice of rows, then the (4x smaller) level is gathered over NVLink
+                oh, ow = (cur.shape[0] + 1) // 2, (cur.shape[1] + 1) // 2
+                bands = parallel.split_even(oh, self.comm.world)
+                nxt = torch.empty((oh, ow), dtype=cur.dtype, device=cur.device)
+                ops.pyr_down_rows(cur, bands[self.comm.rank], nxt)
+                cur = self.comm.gather_rows(nxt, bands)
+            else:
+                cur = ops.pyr_down(cur)
             pyr.append(cur)
             factors.append(factor)
         pyr.reverse()
@@ -94,7 +139,7 @@ class Engine:
     def dog_rows(self, img: torch.Tensor, L: LevelLayout, rows: Range, banded: bool) -> torch.Tensor:
         """uint8 DoG of `img`, valid on `rows`.  banded: img itself only exists in bands (its global
         min/max must be reduced); otherwise img is replicated and its min/max is computed locally."""
-        if L.sharded and banded:
+        if L.sharded:   # every rank scans its own band only (also for replicated images), then one all-reduce
             mm = self.comm.allreduce_minmax(ops.minmax_rows(img, L.band))
         else:
             mm = ops.minmax_rows(img, (0, L.h))
@@ -133,8 +178,9 @@ class Engine:
     # ------------------------------------------------------------------ register()
     def register(self, ref: torch.Tensor, mov: torch.Tensor) -> torch.Tensor:
         comm, T, ov = self.comm, self.T, self.ov
-        ref_pyr, factors = self.pyramid(ref)
-        mov_pyr, _ = self.pyramid(mov)
+        with self.phase("pyramid"):
+            ref_pyr, factors = self.pyramid(ref)
+            mov_pyr, _ = self.pyramid(mov)
         full = LevelLayout(ref.shape[0], ref.shape[1], T, ov, comm)
         layouts = [LevelLayout(p.shape[0], p.shape[1], T, ov, comm) for p in ref_pyr]
         num_lvl = len(factors)
@@ -151,45 +197,64 @@ class Engine:
             win_rows = _clip(B[0] - ov, B[1] + ov, L.h) if L.sharded else (0, L.h)
             if B[1] <= B[0]:                                       # more ranks than tile rows: nothing to do here
                 gate_rows = win_rows = (B[0], B[0])
+            fb_rows = L.fb_window_rows()[L.rank] if L.sharded else (0, L.h)   # rows my Farneback tiles read
 
             mov_l = mov_pyr[lvl]
             mov_banded = False
             if lvl > 0:
                 if L.sharded:
-                    comm.exchange_rows(m_flow, L.bands, L.grow(ov, ov))      # merge reads tile windows
-                mov_l = self.warp_rows(mov_l, m_flow, L, B)
+                    with self.phase("exchange"):
+                        comm.exchange_rows(m_flow, L.bands, L.grow(ov, ov))      # merge reads tile windows
+                with self.phase("warp"):
+                    mov_l = self.warp_rows(mov_l, m_flow, L, B)
                 mov_banded = L.sharded
                 if L.sharded:
-                    comm.exchange_rows(mov_l, L.bands, L.grow(halo, halo))
+                    dh = 20 if self.use_dog else 0
+                    need = [b if a[1] <= a[0] else (_union(a, b) if b[1] > b[0] else a)
+                            for a, b in zip(L.grow(halo, halo), L.fb_window_rows(dh))]
+                    with self.phase("exchange"):
+                        comm.exchange_rows(mov_l, L.bands, need)
 
             # the reference DoG image serves the flow (if use_dog) and the gate (always)
-            ref_dog_rows = _union(gate_rows, win_rows) if self.use_dog else gate_rows
-            ref_dog = self.dog_rows(ref_pyr[lvl], L, ref_dog_rows, banded=False)
-            fb_ref = ref_dog if self.use_dog else ref_pyr[lvl]
-            fb_mov = self.dog_rows(mov_l, L, win_rows, banded=mov_banded) if self.use_dog else mov_l
+            ref_dog_rows = gate_rows
+            if self.use_dog and fb_rows[1] > fb_rows[0]:
+                ref_dog_rows = _union(gate_rows, fb_rows) if gate_rows[1] > gate_rows[0] else fb_rows
+            with self.phase("dog"):
+                ref_dog = self.dog_rows(ref_pyr[lvl], L, ref_dog_rows, banded=False)
+                fb_ref = ref_dog if self.use_dog else ref_pyr[lvl]
+                fb_mov = self.dog_rows(mov_l, L, fb_rows, banded=mov_banded) if self.use_dog else mov_l
             this_flow = torch.empty((L.h, L.w, 2), dtype=torch.float32, device=ref.device)
-            if L.tiled:
-                tr = L.tile_rows[L.rank]
-                ops.farneback_tiles(fb_mov, fb_ref, T, ov, self.win, self.iters, (tr[0] * L.nx, tr[1] * L.nx), out=this_flow)
-            else:
-                ops.farneback_tiles(fb_mov, fb_ref, 0, 0, self.win, self.iters, out=this_flow)
+            with self.phase("farneback" if L.tiled else "farneback(untiled level)"):
+                if L.tiled:
+                    ops.farneback_tiles(fb_mov, fb_ref, T, ov, self.win, self.iters, L.fb_tiles[L.rank], out=this_flow)
+                else:
+                    ops.farneback_tiles(fb_mov, fb_ref, 0, 0, self.win, self.iters, out=this_flow)
             del fb_mov, fb_ref
-            if L.sharded:
-                comm.exchange_rows(this_flow, L.bands, L.grow(ov, ov))
+            if L.sharded:   # tile centres -> the row bands (+ overlap) the row-wise stages work on
+                with self.phase("exchange"):
+                    comm.exchange_rects(this_flow, L.fb_rects(), L.grow(ov, ov))
 
-            warped = self.warp_rows(mov_l, this_flow, L, B)
+            with self.phase("warp"):
+                warped = self.warp_rows(mov_l, this_flow, L, B)
             del mov_l
             if L.sharded:
-                comm.exchange_rows(warped, L.bands, L.grow(20, over + 20))
-            after = self.mi_scores(ref_dog, self.dog_rows(warped, L, gate_rows, banded=L.sharded), L)
+                with self.phase("exchange"):
+                    comm.exchange_rows(warped, L.bands, L.grow(20, over + 20))
+            with self.phase("dog"):
+                wd = self.dog_rows(warped, L, gate_rows, banded=L.sharded)
+                od = self.dog_rows(mov_pyr[lvl], L, gate_rows, banded=False)
             del warped
-            before = self.mi_scores(ref_dog, self.dog_rows(mov_pyr[lvl], L, gate_rows, banded=False), L)
-            del ref_dog
+            with self.phase("nmi gate"):
+                after = self.mi_scores(ref_dog, wd, L)
+                before = self.mi_scores(ref_dog, od, L)
+            del ref_dog, wd, od
             self.log("    MI score after:", after, "| MI score before:", before)
             better = after > before
             self.decisions.append(dict(factor=factor, mi_after=after, mi_before=before, better=better))
             Ln = layouts[lvl + 1] if lvl + 1 < num_lvl else None
 
+            tail = self.phase("merge+pyrup")
+            tail.__enter__()
             if better:
                 self.log("    Better alignment than before")
                 if lvl == 0:
@@ -216,13 +281,16 @@ class Engine:
                         m_flow, m_layout = self.pyr_up(m_flow, L, full, 2.0), full
                 else:
                     m_flow, m_layout = self.pyr_up(m_flow, L, Ln, 4.0), Ln
+            tail.__exit__(None, None, None)
             del this_flow
 
         if m_flow is None:
             # no pyramid level at all: the reference fails on its unbound local (optflow_registrator.py:173)
             raise UnboundLocalError("cannot access local variable 'm_flow' where it is not associated with a value")
-        if m_layout is not None and m_layout.sharded:
-            comm.gather_rows(m_flow, m_layout.bands)
+        self.flow_layout = m_layout
+        if self.gather_flow and m_layout is not None and m_layout.sharded:
+            with self.phase("gather flow"):
+                comm.gather_rows(m_flow, m_layout.bands)
         return m_flow
 
     def _upscale_to_full(self, flow: torch.Tensor, L: LevelLayout, full: LevelLayout, factor: int):
@@ -247,6 +315,9 @@ class Engine:
             tr = self.comm.tile_row_bands(L.ny)
             bands = [_clip(a * self.T, b * self.T, L.h) for a, b in tr]
             out = torch.empty_like(img)
-            ops.warp_tiles_rows(img, flow, self.T, self.ov, bands[self.comm.rank], out)
-            return self.comm.gather_rows(out, bands)
+            with self.phase("warp"):
+                ops.warp_tiles_rows(img, flow, self.T, self.ov, bands[self.comm.rank], out)
+            with self.phase("gather image"):
+                self.comm.gather_rows(out, bands)
+            return out
         return ops.warp_tiles(img, flow, self.T, self.ov)

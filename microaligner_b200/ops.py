@@ -98,6 +98,15 @@ def pyr_down(img: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def pyr_down_rows(img: torch.Tensor, rows, out: torch.Tensor) -> torch.Tensor:
+    """Rows [rows[0], rows[1]) of cv.pyrDown(img) written into `out` ((h+1)//2, (w+1)//2)."""
+    h, w = img.shape
+    es = img.element_size()
+    check(lib.ma_pyrdown_rows(img.data_ptr(), w * es, h, w, _code(img), out.data_ptr(), out.shape[1] * es, int(rows[0]),
+                              int(rows[1]), _stream()), "ma_pyrdown_rows")
+    return out
+
+
 def pyr_up_flow(flow: torch.Tensor, dsize_hw: Sequence[int], scale: float = 1.0) -> torch.Tensor:
     _req(flow, "flow")
     h, w, _ = flow.shape

@@ -37,6 +37,9 @@ class OptFlowRegistrator:
         # numpy results are read-only and stay mirrored on the device (ops.to_host): handing the flow to
         # Warper.flow then needs no upload.  Set False for a plain writeable array, as the reference returns.
         self.mirror_flow = True
+        # multi-GPU only (parallel.init): False leaves a device-resident flow sharded -- each rank's tensor is
+        # valid on its own band of tile rows, which is all Warper.warp() on the same ranks needs
+        self.gather_flow = True
 
     @property
     def ref_img(self):
@@ -144,6 +147,7 @@ class OptFlowRegistrator:
         self._full_shape = tuple(ref.shape)
         eng = Engine(self.tile_size, self.overlap, self.num_pyr_lvl, self.num_iterations, self.use_full_res_img,
                      self.use_dog, comm=parallel.get())
+        eng.gather_flow = self.gather_flow or host_result
         m_flow = eng.register(ref, mov)     # the coarse-to-fine loop, sharded over the ranks of parallel.get()
         self.decisions = eng.decisions
         return ops.to_host(m_flow, mirror=self.mirror_flow) if host_result else m_flow

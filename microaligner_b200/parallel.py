@@ -58,6 +58,59 @@ def transfer_plan(owned: Sequence[Range], need: Sequence[Range]) -> List[Tuple[i
     return plan
 
 
+Rect = Tuple[int, int, int, int]  # y0, y1, x0, x1
+
+
+def tile_range_rects(tiles: Range, nx: int, T: int, h: int, w: int) -> List[Rect]:
+    """Centres of the row-major tile range [tiles) as at most three rectangles (head of the first tile row,
+    the full rows in between, tail of the last tile row)."""
+    t0, t1 = tiles
+    out = []
+    while t0 < t1:
+        i, j = divmod(t0, nx)
+        if j == 0 and t1 - t0 >= nx:                       # whole tile rows
+            rows = (t1 - t0) // nx
+            out.append((i * T, min((i + rows) * T, h), 0, w))
+            t0 += rows * nx
+        else:                                              # partial tile row
+            j1 = min(nx, j + (t1 - t0))
+            out.append((i * T, min((i + 1) * T, h), j * T, min(j1 * T, w)))
+            t0 += j1 - j
+    return out
+
+
+def rect_plan(have: Sequence[Sequence[Rect]], owned_rows: Sequence[Range], need_rows: Sequence[Range]):
+    """(src, dst, rect): the part of every rectangle rank `src` holds that rank `dst` needs (full-width row
+    range need_rows[dst]) and does not hold itself."""
+    plan = []
+    for dst, nd in enumerate(need_rows):
+        if nd[1] <= nd[0]:
+            continue
+        for src, rects in enumerate(have):
+            if src == dst:
+                continue
+            for (y0, y1, x0, x1) in rects:
+                rows = intersect((y0, y1), nd)
+                if rows[1] <= rows[0]:
+                    continue
+                # drop what dst computed itself
+                pieces = [(rows[0], rows[1], x0, x1)]
+                for (a0, a1, b0, b1) in have[dst]:
+                    nxt = []
+                    for (p0, p1, q0, q1) in pieces:
+                        ry, rx = intersect((p0, p1), (a0, a1)), intersect((q0, q1), (b0, b1))
+                        if ry[1] <= ry[0] or rx[1] <= rx[0]:
+                            nxt.append((p0, p1, q0, q1))
+                            continue
+                        for (u0, u1) in subtract((p0, p1), ry):
+                            nxt.append((u0, u1, q0, q1))
+                        for (v0, v1) in subtract((q0, q1), rx):
+                            nxt.append((ry[0], ry[1], v0, v1))
+                    pieces = nxt
+                plan.extend((src, dst, r) for r in pieces)
+    return plan
+
+
 def chunk_range_of_band(band: Range, w: int, chunk: int, n: int) -> Range:
     """NMI chunks (runs of `chunk` row-major elements of an image of width w, n elements in total)
     whose first element lies in image rows [band)."""
@@ -102,6 +155,34 @@ class Comm:
                 buf = torch.empty(view.shape, dtype=view.dtype, device="cpu") if stage_cpu else view
                 ops.append(dist.P2POp(dist.irecv, buf, src, group=self.group))
                 if stage_cpu:
+                    recvs.append((view, buf))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        for view, buf in recvs:
+            view.copy_(buf)
+        return t
+
+    def exchange_rects(self, t: torch.Tensor, have: Sequence[Sequence[Rect]], need_rows: Sequence[Range]):
+        """Rank q holds the rectangles have[q] of `t` (rows x columns); make rows need_rows[rank] valid here."""
+        if self.world == 1:
+            return t
+        mine = [p for p in rect_plan(have, None, need_rows) if self.rank in (p[0], p[1])]
+        if not mine:
+            return t
+        tw = self._wire(t)
+        scale = tw.shape[1] // t.shape[1]                  # uint16 images travel as bytes: 2 columns per pixel
+        cpu = self.backend == "gloo" and t.is_cuda
+        ops, recvs = [], []
+        for src, dst, (y0, y1, x0, x1) in mine:
+            view = tw[y0:y1, x0 * scale:x1 * scale]
+            if src == self.rank:
+                buf = view.contiguous()
+                ops.append(dist.P2POp(dist.isend, buf.cpu() if cpu else buf, dst, group=self.group))
+            else:
+                direct = view.is_contiguous() and not cpu
+                buf = view if direct else torch.empty(view.shape, dtype=view.dtype, device="cpu" if cpu else view.device)
+                ops.append(dist.P2POp(dist.irecv, buf, src, group=self.group))
+                if not direct:
                     recvs.append((view, buf))
         for req in dist.batch_isend_irecv(ops):
             req.wait()
