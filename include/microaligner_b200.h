@@ -100,13 +100,16 @@ int ma_dog_u8(const void* src, size_t src_pitch, int dtype, int h, int w,
 
 /* The two phases of ma_dog_u8 on a band of rows, for row-sharded execution: the caller supplies the
  * GLOBAL min/max of the source (device float[2]) and later of the difference image (after reducing the
- * per-band values ma_dog_diff_rows returns in diff_minmax).  diff is an (h, ma_dog_diff_pitch_floats(w))
- * float plane; source rows [row_begin-20, row_end+20) must be valid. */
+ * per-band values ma_dog_diff_rows returns in diff_minmax).  Memory scales with the band, not the image:
+ * `diff` holds rows [row_begin, row_end) only ((row_end-row_begin) x ma_dog_diff_pitch_floats(w) floats) and
+ * the workspace is ma_dog_band_workspace_bytes(w, row_end-row_begin).  Source rows [row_begin-20,
+ * row_end+20) must be valid.  ma_dog_quantize_rows reads a diff plane whose first row is image row diff_row0. */
 size_t ma_dog_diff_pitch_floats(int w);
+size_t ma_dog_band_workspace_bytes(int w, int nrows);
 int ma_dog_diff_rows(const void* src, size_t src_pitch, int dtype, int h, int w, const float* src_minmax,
                      int row_begin, int row_end, float* diff, float* diff_minmax, void* workspace, void* stream);
-int ma_dog_quantize_rows(const float* diff, int h, int w, const float* diff_minmax, int row_begin, int row_end,
-                         uint8_t* dst, size_t dst_pitch, void* stream);
+int ma_dog_quantize_rows(const float* diff, int diff_row0, int h, int w, const float* diff_minmax, int row_begin,
+                         int row_end, uint8_t* dst, size_t dst_pitch, void* stream);
 
 /* ---- mi_tiled (shared_modules/similarity_scoring.py:27-50): normalized mutual information
  * (sklearn, arithmetic mean, natural log) of two u8 label images over consecutive chunks of

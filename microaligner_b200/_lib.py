@@ -36,7 +36,8 @@ PROTOTYPES = {
     "ma_merge_flows_tile_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "ma_dog_diff_pitch_floats": (c_size_t, [c_int]),
     "ma_dog_diff_rows": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "ma_dog_quantize_rows": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "ma_dog_band_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "ma_dog_quantize_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "ma_nmi_chunk_range": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_size_t, c_size_t, c_void_p, c_void_p, c_void_p]),
     "ma_merge_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "ma_merge_flows_tiles": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),

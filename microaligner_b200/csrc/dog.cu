@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(DOG_HT) dog_row_kernel(const T* __restrict__ s
                                                          const float* __restrict__ src_mm,
                                                          float* __restrict__ A5, float* __restrict__ A9, int wp,
                                                          const __grid_constant__ DogTaps taps, int ybeg, int yend) {
+    // A5 / A9 hold image rows [ybeg, yend) only: plane row = y - ybeg
     __shared__ __align__(16) float seg[2][DOG_SEG];
     const int xb = blockIdx.x * DOG_HW;
     const int y_first = ybeg + blockIdx.y * DOG_HROWS;
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(DOG_HT) dog_row_kernel(const T* __restrict__ s
                     s9[o] = __fadd_rn(s9[o], __fmul_rn(in[o + j], taps.k9[j]));
                 }
         }
-        const size_t o = (size_t)y * wp + x0;
+        const size_t o = (size_t)(y - ybeg) * wp + x0;
         if (x0 + 3 < w) {
             *reinterpret_cast<float4*>(A5 + o) = make_float4(s5[0], s5[1], s5[2], s5[3]);
             *reinterpret_cast<float4*>(A9 + o) = make_float4(s9[0], s9[1], s9[2], s9[3]);
@@ -238,7 +239,8 @@ __device__ __forceinline__ void col_conv8x2(const u64* __restrict__ centre, cons
 
 __global__ void __launch_bounds__(256) dog_col_kernel(const __grid_constant__ CUtensorMap mapA, int wp, int h, int w,
                                                       float* __restrict__ D, unsigned* keys_out,
-                                                      const __grid_constant__ DogTaps taps, int ybeg, int yend) {
+                                                      const __grid_constant__ DogTaps taps, int ybeg, int yend, int plane_row0) {
+    // the TMA planes hold image rows from plane_row0 on; D holds rows [ybeg, yend) (row = y - ybeg)
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t bar;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -253,8 +255,8 @@ __global__ void __launch_bounds__(256) dog_col_kernel(const __grid_constant__ CU
     __syncthreads();
     if (threadIdx.x == 0) {
         mbar_expect_tx(&bar, 2 * DC_ROWS * 64 * sizeof(float));
-        tma_load_3d(buf5, &mapA, x0, v_first, 0, &bar);
-        tma_load_3d(buf9, &mapA, x0, v_first, 1, &bar);
+        tma_load_3d(buf5, &mapA, x0, v_first - plane_row0, 0, &bar);
+        tma_load_3d(buf9, &mapA, x0, v_first - plane_row0, 1, &bar);
     }
     mbar_wait(&bar, 0);
     if (v_first < 0 || v_first + DC_ROWS > h) {  // CTA-uniform: mirror the rows outside the image
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(256) dog_col_kernel(const __grid_constant__ CU
             const int y = y0 + o0 + j;
             if (y < yend) {
                 float2 d = unpack2(sub2(s9[j], s5[j]));
-                float* out = D + (size_t)y * wp + x;
+                float* out = D + (size_t)(y - ybeg) * wp + x;
                 if (x + 1 < w) {
                     *reinterpret_cast<float2*>(out) = d;
                     lo = fminf(lo, fminf(d.x, d.y));
@@ -304,12 +306,13 @@ __global__ void __launch_bounds__(256) dog_col_kernel(const __grid_constant__ CU
 }
 
 __global__ void __launch_bounds__(256) dog_quant_kernel(const float* __restrict__ D, int wp, int h, int w,
-                                                        const float* __restrict__ mm, uint8_t* __restrict__ dst, size_t dp, int ybeg) {
+                                                        const float* __restrict__ mm, uint8_t* __restrict__ dst, size_t dp, int ybeg,
+                                                        int d_row0) {
     float a, b;
     norm255_coeffs(mm, a, b);
     int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = ybeg + blockIdx.y;
     if (x >= w) return;
-    const float* row = D + (size_t)y * wp;
+    const float* row = D + (size_t)(y - d_row0) * wp;
     uint8_t* out = dst + (size_t)y * dp;
     auto q = [&](float d) { return (uint8_t)max(0, min(255, __float2int_rn(__fmaf_rn(d, a, b)))); };
     if (x + 3 < w && ((dp & 3) == 0) && ((((uintptr_t)dst) & 3) == 0)) {
@@ -390,6 +393,12 @@ extern "C" size_t ma_dog_workspace_bytes(int h, int w) {
 
 extern "C" size_t ma_dog_diff_pitch_floats(int w) { return (size_t)pad4(w); }
 
+// scratch of ma_dog_diff_rows for a band of `nrows` rows: keys + two row-filtered planes of nrows + 40 rows
+extern "C" size_t ma_dog_band_workspace_bytes(int w, int nrows) {
+    if (w <= 0 || nrows < 0) return 0;
+    return 256 + 2 * (size_t)(nrows + 40) * pad4(w) * sizeof(float);
+}
+
 // phase 1: rows [row_begin, row_end) of d = blur9(f) - blur5(f), f = normalised src, plus min/max of those rows
 extern "C" int ma_dog_diff_rows(const void* src, size_t src_pitch, int dtype, int h, int w, const float* src_minmax,
                                 int row_begin, int row_end, float* diff, float* diff_minmax, void* workspace, void* stream) {
@@ -400,14 +409,14 @@ extern "C" int ma_dog_diff_rows(const void* src, size_t src_pitch, int dtype, in
     cudaStream_t s = (cudaStream_t)stream;
     unsigned* keys = (unsigned*)workspace;
     int wp = pad4(w);
+    const int ra = std::max(row_begin - 20, 0), rb = std::min(row_end + 20, h);   // rows the row pass produces
     float* A5 = (float*)((char*)workspace + 256);
-    float* A9 = A5 + (size_t)h * wp;
+    float* A9 = A5 + (size_t)(rb - ra) * wp;
     static DogTaps taps;
     static bool taps_ready = false;
     if (!taps_ready) { make_dog_taps(taps); taps_ready = true; }
     { KernelScope ks(K_SMALL, s); init_minmax_keys<<<1, 32, 0, s>>>(keys, 1); }
     if (row_begin < row_end) {
-        int ra = std::max(row_begin - 20, 0), rb = std::min(row_end + 20, h);
         double px = (double)(row_end - row_begin) * w;
         dim3 rg(ceil_div(w, DOG_HW), ceil_div(rb - ra, DOG_HROWS)), rbk(DOG_HT);
         { KernelScope ks(K_DOG_ROW, s, px);
@@ -415,7 +424,7 @@ extern "C" int ma_dog_diff_rows(const void* src, size_t src_pitch, int dtype, in
         else dog_row_kernel<uint16_t><<<rg, rbk, 0, s>>>((const uint16_t*)src, src_pitch, h, w, src_minmax, A5, A9, wp, taps, ra, rb); }
         { KernelScope ks(K_DOG_COL, s, px);
         CUtensorMap mapA;
-        if (!make_plane_map(&mapA, A5, (uint64_t)w, (uint64_t)h, 2, (uint64_t)wp * 4, (uint64_t)h * wp * 4, 64, DC_ROWS)) {
+        if (!make_plane_map(&mapA, A5, (uint64_t)w, (uint64_t)(rb - ra), 2, (uint64_t)wp * 4, (uint64_t)(rb - ra) * wp * 4, 64, DC_ROWS)) {
             set_error("ma_dog_diff_rows: cuTensorMapEncodeTiled failed");
             return MA_ERR_CUDA;
         }
@@ -425,7 +434,7 @@ extern "C" int ma_dog_diff_rows(const void* src, size_t src_pitch, int dtype, in
             attr_set = true;
         }
         dog_col_kernel<<<dim3(ceil_div(w, 64), ceil_div(row_end - row_begin, DC_OUT)), 256, 2 * DC_ROWS * 64 * 4, s>>>(
-            mapA, wp, h, w, diff, keys, taps, row_begin, row_end); }
+            mapA, wp, h, w, diff, keys, taps, row_begin, row_end, ra); }
     }
     { KernelScope ks(K_SMALL, s); keys_to_float_kernel<<<1, 1, 0, s>>>(keys, diff_minmax); }
     MA_LAUNCH_CHECK("dog diff kernels");
@@ -433,14 +442,14 @@ extern "C" int ma_dog_diff_rows(const void* src, size_t src_pitch, int dtype, in
 }
 
 // phase 2: rows [row_begin, row_end) of the u8 result from d and the GLOBAL min/max of d
-extern "C" int ma_dog_quantize_rows(const float* diff, int h, int w, const float* diff_minmax, int row_begin, int row_end,
-                                    uint8_t* dst, size_t dst_pitch, void* stream) {
+extern "C" int ma_dog_quantize_rows(const float* diff, int diff_row0, int h, int w, const float* diff_minmax, int row_begin,
+                                    int row_end, uint8_t* dst, size_t dst_pitch, void* stream) {
     if (!diff || !diff_minmax || !dst) return invalid("ma_dog_quantize_rows: null pointer");
-    if (row_begin < 0 || row_end > h || row_begin > row_end) return invalid("ma_dog_quantize_rows: bad row range");
+    if (row_begin < diff_row0 || row_end > h || row_begin > row_end) return invalid("ma_dog_quantize_rows: bad row range");
     if (row_begin == row_end) return MA_OK;
     cudaStream_t s = (cudaStream_t)stream;
     KernelScope ks(K_DOG_QUANT, s, (double)(row_end - row_begin) * w);
-    dog_quant_kernel<<<dim3(ceil_div(ceil_div(w, 4), 256), row_end - row_begin), 256, 0, s>>>(diff, pad4(w), h, w, diff_minmax, dst, dst_pitch, row_begin);
+    dog_quant_kernel<<<dim3(ceil_div(ceil_div(w, 4), 256), row_end - row_begin), 256, 0, s>>>(diff, pad4(w), h, w, diff_minmax, dst, dst_pitch, row_begin, diff_row0);
     MA_LAUNCH_CHECK("dog_quant_kernel");
     return MA_OK;
 }
@@ -455,7 +464,7 @@ extern "C" int ma_dog_u8(const void* src, size_t src_pitch, int dtype, int h, in
     if (rc) return rc;
     rc = ma_dog_diff_rows(src, src_pitch, dtype, h, w, mm, 0, h, D, mm + 2, workspace, stream);
     if (rc) return rc;
-    return ma_dog_quantize_rows(D, h, w, mm + 2, 0, h, dst, dst_pitch, stream);
+    return ma_dog_quantize_rows(D, 0, h, w, mm + 2, 0, h, dst, dst_pitch, stream);
 }
 
 extern "C" size_t ma_zmip_workspace_bytes(int h, int w, int dtype) {

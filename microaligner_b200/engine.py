@@ -118,7 +118,7 @@ class Engine:
             factor = 2 ** (lvl + 1)
             if arr.shape[0] / factor < 100 or arr.shape[1] / factor < 100:
                 break
-            if self.comm.world > 1 and cur.shape[0] >= 64 * self.comm.world:
+            if self.comm.world > 1 and cur.shape[0] >= 16384:   # below that the gather latency outweighs the saving
                 # every rank reduces its slice of rows, then the (4x smaller) level is gathered over NVLink
                 oh, ow = (cur.shape[0] + 1) // 2, (cur.shape[1] + 1) // 2
                 bands = parallel.split_even(oh, self.comm.world)
@@ -136,36 +136,47 @@ class Engine:
             factors.append(1)
         return pyr, factors
 
-    def dog_rows(self, img: torch.Tensor, L: LevelLayout, rows: Range, banded: bool) -> torch.Tensor:
-        """uint8 DoG of `img`, valid on `rows`.  banded: img itself only exists in bands (its global
-        min/max must be reduced); otherwise img is replicated and its min/max is computed locally."""
-        if L.sharded:   # every rank scans its own band only (also for replicated images), then one all-reduce
-            mm = self.comm.allreduce_minmax(ops.minmax_rows(img, L.band))
-        else:
-            mm = ops.minmax_rows(img, (0, L.h))
-        diff, dmm = ops.dog_diff_rows(img, mm, rows)
+    def dog_batch(self, items, L: LevelLayout) -> List[torch.Tensor]:
+        """uint8 DoG of several images of one level: items = [(img, rows)], result i valid on rows_i.
+        Sharded levels need the GLOBAL min/max of every source and of every difference image: every rank
+        scans its own band, and all pairs of the batch travel in ONE all-reduce per phase."""
+        k = len(items)
+        dev = items[0][0].device
+        mm = torch.empty((k, 2), dtype=torch.float32, device=dev)
+        dmm = torch.empty((k, 2), dtype=torch.float32, device=dev)
+        for i, (img, rows) in enumerate(items):
+            ops.minmax_rows(img, L.band if L.sharded else (0, L.h), out=mm[i])
+        if L.sharded:
+            self.comm.allreduce_minmax(mm)
+        diffs = [ops.dog_diff_rows(img, mm[i], rows, dmm=dmm[i])[0] for i, (img, rows) in enumerate(items)]
         if L.sharded:
             self.comm.allreduce_minmax(dmm)
-        out = torch.empty((L.h, L.w), dtype=torch.uint8, device=img.device)
-        return ops.dog_quantize_rows(diff, L.w, dmm, rows, out)
+        outs = []
+        for i, (img, rows) in enumerate(items):
+            out = torch.empty((L.h, L.w), dtype=torch.uint8, device=dev)
+            outs.append(ops.dog_quantize_rows(diffs[i], L.h, L.w, dmm[i], rows, out))
+        return outs
 
     def warp_rows(self, img: torch.Tensor, flow: torch.Tensor, L: LevelLayout, rows: Range) -> torch.Tensor:
         out = torch.empty_like(img)
         return ops.warp_tiles_rows(img, flow, self.T, self.ov, rows, out)
 
-    def mi_scores(self, a: torch.Tensor, b: torch.Tensor, L: LevelLayout) -> float:
-        """mi_tiled (similarity_scoring.py:27-50)."""
+    def mi_scores(self, a: torch.Tensor, bs: Sequence[torch.Tensor], L: LevelLayout) -> List[float]:
+        """mi_tiled(a, b) for every b in bs (similarity_scoring.py:27-50): per-chunk NMI on the device, one
+        all-reduce and one read-back for the whole batch, np.mean on the host (rounds like the reference)."""
         n = a.numel()
         if not L.tiled:
-            return float(ops.nmi_chunks(a, b, n).cpu().numpy()[0])
+            return [float(ops.nmi_chunks(a, b, n).cpu().numpy()[0]) for b in bs]
         chunk = self.T * self.T
         nchunks = -(-n // chunk)
-        scores = torch.zeros(nchunks, dtype=torch.float64, device=a.device)
+        scores = torch.zeros((len(bs), nchunks), dtype=torch.float64, device=a.device)
         cr = parallel.chunk_range_of_band(L.band, L.w, chunk, n) if L.sharded else (0, nchunks)
-        ops.nmi_chunk_range(a, b, chunk, cr, scores)
+        for i, b in enumerate(bs):
+            ops.nmi_chunk_range(a, b, chunk, cr, scores[i])
         if L.sharded:
             self.comm.allreduce_sum(scores)
-        return float(np.mean(scores.cpu().numpy()))
+        host = scores.cpu().numpy()
+        return [float(np.mean(host[i])) for i in range(len(bs))]
 
     def pyr_up(self, flow: torch.Tensor, Ls: LevelLayout, Ld: LevelLayout, scale: float) -> torch.Tensor:
         """cv.pyrUp(flow*scale) from level Ls to level Ld; every rank produces the rows of its Ld band."""
@@ -220,9 +231,15 @@ class Engine:
             if self.use_dog and fb_rows[1] > fb_rows[0]:
                 ref_dog_rows = _union(gate_rows, fb_rows) if gate_rows[1] > gate_rows[0] else fb_rows
             with self.phase("dog"):
-                ref_dog = self.dog_rows(ref_pyr[lvl], L, ref_dog_rows, banded=False)
+                # batch 1: everything that does not depend on this level's flow
+                items = [(ref_pyr[lvl], ref_dog_rows), (mov_pyr[lvl], gate_rows)]
+                if self.use_dog:
+                    items.append((mov_l, fb_rows))
+                dogs = self.dog_batch(items, L)
+                ref_dog, od = dogs[0], dogs[1]
                 fb_ref = ref_dog if self.use_dog else ref_pyr[lvl]
-                fb_mov = self.dog_rows(mov_l, L, fb_rows, banded=mov_banded) if self.use_dog else mov_l
+                fb_mov = dogs[2] if self.use_dog else mov_l
+                del dogs, items
             this_flow = torch.empty((L.h, L.w, 2), dtype=torch.float32, device=ref.device)
             with self.phase("farneback" if L.tiled else "farneback(untiled level)"):
                 if L.tiled:
@@ -241,12 +258,10 @@ class Engine:
                 with self.phase("exchange"):
                     comm.exchange_rows(warped, L.bands, L.grow(20, over + 20))
             with self.phase("dog"):
-                wd = self.dog_rows(warped, L, gate_rows, banded=L.sharded)
-                od = self.dog_rows(mov_pyr[lvl], L, gate_rows, banded=False)
+                wd = self.dog_batch([(warped, gate_rows)], L)[0]
             del warped
             with self.phase("nmi gate"):
-                after = self.mi_scores(ref_dog, wd, L)
-                before = self.mi_scores(ref_dog, od, L)
+                after, before = self.mi_scores(ref_dog, [wd, od], L)
             del ref_dog, wd, od
             self.log("    MI score after:", after, "| MI score before:", before)
             better = after > before

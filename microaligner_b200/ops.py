@@ -262,10 +262,11 @@ def merge_flows_tile_rows(f1, f2, tile_size, overlap, tile_rows, out):
     return out
 
 
-def minmax_rows(img, rows):
+def minmax_rows(img, rows, out=None):
     """[min, max] (float32 device tensor) of image rows [rows[0], rows[1])."""
     h, w = img.shape
-    out = torch.empty(2, dtype=torch.float32, device=img.device)
+    if out is None:
+        out = torch.empty(2, dtype=torch.float32, device=img.device)
     if rows[1] <= rows[0]:
         out[0], out[1] = float("inf"), float("-inf")
         return out
@@ -275,22 +276,26 @@ def minmax_rows(img, rows):
     return out
 
 
-def dog_diff_rows(img, src_minmax, rows):
-    """Rows of the un-normalised difference of Gaussians + their [min, max]; see ma_dog_diff_rows."""
+def dog_diff_rows(img, src_minmax, rows, dmm=None):
+    """Rows [rows) of the un-normalised difference of Gaussians (band-sized plane: row 0 = image row rows[0])
+    and their [min, max]; see ma_dog_diff_rows."""
     h, w = img.shape
+    n = max(int(rows[1] - rows[0]), 0)
     wp = lib.ma_dog_diff_pitch_floats(w)
-    diff = torch.empty((h, wp), dtype=torch.float32, device=img.device)
-    dmm = torch.empty(2, dtype=torch.float32, device=img.device)
-    ws = _bytes(lib.ma_dog_workspace_bytes(h, w), img.device)
+    diff = torch.empty((max(n, 1), wp), dtype=torch.float32, device=img.device)
+    if dmm is None:
+        dmm = torch.empty(2, dtype=torch.float32, device=img.device)
+    ws = _bytes(lib.ma_dog_band_workspace_bytes(w, n), img.device)
     check(lib.ma_dog_diff_rows(img.data_ptr(), w * img.element_size(), _code(img), h, w, src_minmax.data_ptr(), int(rows[0]),
-                               int(rows[1]), diff.data_ptr(), dmm.data_ptr(), ws.data_ptr(), _stream()), "ma_dog_diff_rows")
+                               int(rows[0]) + n, diff.data_ptr(), dmm.data_ptr(), ws.data_ptr(), _stream()), "ma_dog_diff_rows")
     return diff, dmm
 
 
-def dog_quantize_rows(diff, w, diff_minmax, rows, out):
-    h = diff.shape[0]
-    check(lib.ma_dog_quantize_rows(diff.data_ptr(), h, int(w), diff_minmax.data_ptr(), int(rows[0]), int(rows[1]),
-                                   out.data_ptr(), int(w), _stream()), "ma_dog_quantize_rows")
+def dog_quantize_rows(diff, h, w, diff_minmax, rows, out):
+    """uint8 rows [rows) from a band-sized diff plane produced by dog_diff_rows for the same rows."""
+    if rows[1] > rows[0]:
+        check(lib.ma_dog_quantize_rows(diff.data_ptr(), int(rows[0]), int(h), int(w), diff_minmax.data_ptr(), int(rows[0]),
+                                       int(rows[1]), out.data_ptr(), int(w), _stream()), "ma_dog_quantize_rows")
     return out
 
 

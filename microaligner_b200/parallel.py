@@ -198,12 +198,12 @@ class Comm:
         return self.exchange_rows(t, owned, [full] * self.world)
 
     def allreduce_minmax(self, mm: torch.Tensor):
-        """mm = [min, max] float32 (device); reduced in place over the group."""
+        """mm = (..., 2) float32 [min, max] pairs (device); reduced in place over the group, one collective."""
         if self.world == 1:
             return mm
-        v = torch.stack([-mm[0], mm[1]])
+        v = torch.stack([-mm[..., 0], mm[..., 1]])
         v = self._allreduce(v, dist.ReduceOp.MAX)
-        mm[0], mm[1] = -v[0], v[1]
+        mm[..., 0], mm[..., 1] = -v[0], v[1]
         return mm
 
     def _allreduce(self, t: torch.Tensor, op):
