@@ -307,7 +307,7 @@ def run_b200(args):
                                       "peak_ginstr_s": fp_peak / 1e9, "frac": fp_ach / fp_peak, "at_sm_mhz": clocks["sm_mhz"]}
     line = {
         "metric": "Mpixel/s registered (Farneback flow + warp)", "value": value, "unit": "Mpx/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": args.scaling,
         "parallelism": f"tile-row bands over {world} GPU(s), P2P halo exchange + scalar all-reduces (NCCL)",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
         "e2e": {"value": e2e_val, "unit": "Mpx/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -343,11 +343,22 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--size", type=int, default=20000)
+    ap.add_argument("--size", type=int, default=None,
+                    help="image side; default: 20000 at 1 GPU (BASELINE configs[1]) growing with the GPU count up to the "
+                         "50000 whole-slide pair of configs[4] at 8 GPUs (weak scaling, image area ~ N)")
+    ap.add_argument("--strong", action="store_true", help="keep the 20000^2 pair at every GPU count (strong scaling)")
     ap.add_argument("--cpu-sample", type=int, default=4000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--trace", action="store_true", help="extra untimed step with per-phase synchronised wall times (stderr)")
     args = ap.parse_args()
+    args.scaling = "weak"
+    if args.size is None:
+        n = max(1, int(os.environ.get("WORLD_SIZE", args.gpus)))
+        args.size = 20000 if (args.strong or n == 1) else min(50000, int(round(20000 * n ** 0.5 / 1000.0)) * 1000)
+        if args.strong:
+            args.scaling = "strong"
+    elif int(os.environ.get("WORLD_SIZE", args.gpus)) > 1:
+        args.scaling = "strong"  # explicit size: the same image at every GPU count
     if args.impl == "reference":
         run_reference(args)
     else:
