@@ -129,37 +129,42 @@ __global__ void __launch_bounds__(256) fb_polyexp_kernel(const T* __restrict__ m
     for (int which = 0; which < 2; ++which) {          // 0: prev = moving -> R0, 1: next = reference -> R1
         const T* img = which ? ref : mov;
         __syncthreads();
-        for (int p = tid; p < PE_RH * PE_RW; p += 256) {
-            int r = p / PE_RW, c = p % PE_RW;
-            int yy = y0 - 2 + r, xx = x0 - 2 + c;
-            float v = 0.0f;
-            if ((unsigned)yy < (unsigned)Sh && (unsigned)xx < (unsigned)Sw) v = window_px(img, pitch, g, oy, ox, yy, xx);
-            raw[r][c] = v;
+        // all staging loops walk columns {tx, tx + 64} and rows ty, ty + 4, ...: no div/mod, and the per-column
+        // border index math (clamp / REFLECT_101) is hoisted out of the row loops
+        for (int c = tx; c < PE_RW; c += 64) {
+            const int xx = x0 - 2 + c, gx = ox + xx;
+            const bool colok = (unsigned)xx < (unsigned)Sw && (unsigned)gx < (unsigned)g.w;
+            for (int r = ty; r < PE_RH; r += 4) {
+                const int yy = y0 - 2 + r, gy = oy + yy;
+                float v = 0.0f;
+                if (colok && (unsigned)yy < (unsigned)Sh && (unsigned)gy < (unsigned)g.h)
+                    v = (float)__ldg((const T*)((const char*)img + (size_t)gy * pitch) + gx);
+                raw[r][c] = v;
+            }
         }
         __syncthreads();
-        for (int p = tid; p < PE_RH * PE_PW; p += 256) {      // rows: actual, columns: replicated positions
-            int r = p / PE_PW, cu = p % PE_PW;
-            int px = min(max(x0 - 1 + cu, 0), Sw - 1);
-            int xl = reflect101(px - 1, Sw), xr = reflect101(px + 1, Sw);
-            const float* row = raw[r] - (x0 - 2);
-            th[r][cu] = __fadd_rn(__fmul_rn(row[px], 0.5f), __fmul_rn(__fadd_rn(row[xl], row[xr]), 0.25f));
+        for (int cu = tx; cu < PE_PW; cu += 64) {                // rows: actual, columns: replicated positions
+            const int px = min(max(x0 - 1 + cu, 0), Sw - 1);
+            const int ic = px - (x0 - 2), il = reflect101(px - 1, Sw) - (x0 - 2), ir = reflect101(px + 1, Sw) - (x0 - 2);
+            for (int r = ty; r < PE_RH; r += 4)
+                th[r][cu] = __fadd_rn(__fmul_rn(raw[r][ic], 0.5f), __fmul_rn(__fadd_rn(raw[r][il], raw[r][ir]), 0.25f));
         }
         __syncthreads();
-        for (int p = tid; p < PE_PH * PE_PW; p += 256) {
-            int rv = p / PE_PW, cu = p % PE_PW;
-            int py = min(max(y0 - 1 + rv, 0), Sh - 1);
-            int yu = reflect101(py - 1, Sh), yd = reflect101(py + 1, Sh);
-            const int ro = y0 - 2;
-            P[rv][cu] = __fadd_rn(__fmul_rn(th[py - ro][cu], 0.5f), __fmul_rn(__fadd_rn(th[yu - ro][cu], th[yd - ro][cu]), 0.25f));
+        for (int rv = ty; rv < PE_PH; rv += 4) {
+            const int py = min(max(y0 - 1 + rv, 0), Sh - 1);
+            const int rc = py - (y0 - 2), ru = reflect101(py - 1, Sh) - (y0 - 2), rd = reflect101(py + 1, Sh) - (y0 - 2);
+            for (int cu = tx; cu < PE_PW; cu += 64)
+                P[rv][cu] = __fadd_rn(__fmul_rn(th[rc][cu], 0.5f), __fmul_rn(__fadd_rn(th[ru][cu], th[rd][cu]), 0.25f));
         }
         __syncthreads();
-        for (int p = tid; p < PE_BH * PE_PW; p += 256) {      // vertical pass of the expansion (f32)
-            int r = p / PE_PW, c = p % PE_PW;
-            float s0 = P[r][c], sc = P[r + 1][c], s1 = P[r + 2][c];
-            float pp = __fadd_rn(s0, s1);
-            T0[r][c] = __fadd_rn(__fmul_rn(sc, cst.g0), __fmul_rn(cst.g1, pp));
-            T1[r][c] = __fadd_rn(0.0f, __fmul_rn(cst.xg1, __fsub_rn(s1, s0)));
-            T2[r][c] = __fadd_rn(0.0f, __fmul_rn(cst.xxg1, pp));
+        for (int c = tx; c < PE_PW; c += 64) {                   // vertical pass of the expansion (f32)
+            for (int r = ty; r < PE_BH; r += 4) {
+                float s0 = P[r][c], sc = P[r + 1][c], s1 = P[r + 2][c];
+                float pp = __fadd_rn(s0, s1);
+                T0[r][c] = __fadd_rn(__fmul_rn(sc, cst.g0), __fmul_rn(cst.g1, pp));
+                T1[r][c] = __fadd_rn(0.0f, __fmul_rn(cst.xg1, __fsub_rn(s1, s0)));
+                T2[r][c] = __fadd_rn(0.0f, __fmul_rn(cst.xxg1, pp));
+            }
         }
         __syncthreads();
         const int x = x0 + tx;
