@@ -44,6 +44,8 @@ PROTOTYPES = {
     "ma_farneback_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "ma_farneback_tiles": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                    c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ma_farneback_tiles_ex": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                      c_int, c_int, c_void_p, c_void_p, c_size_t, ctypes.c_uint, c_void_p]),
     "ma_dog_workspace_bytes": (c_size_t, [c_int, c_int]),
     "ma_dog_u8": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "ma_nmi_workspace_bytes": (c_size_t, [c_size_t, c_size_t]),

@@ -22,6 +22,7 @@
 // memory afterwards); each thread keeps 8 packed (f32x2) outputs and two 8-deep packed sliding windows
 // in registers, so shared-memory traffic is 2 LDS.64 per 24 packed FP instructions.
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 #include "common.cuh"
 #include "packed.cuh"
@@ -273,6 +274,9 @@ constexpr int kRowU = kRowF / 2;     // packed pairs per row
 
 // `centre` -> this thread's pair in the row holding the centre tap of output 0; outputs 0..7 are the
 // next rows.  k2[i] = {k[i], k[i]}.
+// FUSED = false: OpenCV's separately rounded multiply and add (bit parity, the default).
+// FUSED = true : acc = fma(a[+i] + a[-i], k[i], acc) -- opt-in, 1.5x fewer FP32 pipe cycles, ~1e-6 px off.
+template <bool FUSED>
 __device__ __forceinline__ void conv8x2(const u64* __restrict__ centre, int m, const float2* __restrict__ k2, u64 nz, u64 (&acc)[kR]) {
     u64 wp[kR], wm[kR];
     const u64 k0 = *reinterpret_cast<const u64*>(&k2[0]);
@@ -295,7 +299,10 @@ __device__ __forceinline__ void conv8x2(const u64* __restrict__ centre, int m, c
             wm[(63 - s) & 7] = pm[-s * kRowU];
             const u64 kk = *reinterpret_cast<const u64*>(&k2[i + s]);
 #pragma unroll
-            for (int j = 0; j < kR; ++j) acc[j] = add2(acc[j], mul2(add2(wp[(j + s + 1) & 7], wm[(j + 63 - s) & 7]), kk, nz));
+            for (int j = 0; j < kR; ++j) {
+                const u64 pr = add2(wp[(j + s + 1) & 7], wm[(j + 63 - s) & 7]);
+                acc[j] = FUSED ? fma2(pr, kk, acc[j]) : add2(acc[j], mul2(pr, kk, nz));
+            }
         }
         pp += kR * kRowU;
         pm -= kR * kRowU;
@@ -307,7 +314,10 @@ __device__ __forceinline__ void conv8x2(const u64* __restrict__ centre, int m, c
             wm[(63 - s) & 7] = pm[-s * kRowU];
             const u64 kk = *reinterpret_cast<const u64*>(&k2[i + s]);
 #pragma unroll
-            for (int j = 0; j < kR; ++j) acc[j] = add2(acc[j], mul2(add2(wp[(j + s + 1) & 7], wm[(j + 63 - s) & 7]), kk, nz));
+            for (int j = 0; j < kR; ++j) {
+                const u64 pr = add2(wp[(j + s + 1) & 7], wm[(j + 63 - s) & 7]);
+                acc[j] = FUSED ? fma2(pr, kk, acc[j]) : add2(acc[j], mul2(pr, kk, nz));
+            }
         }
     }
 }
@@ -333,7 +343,7 @@ __device__ __forceinline__ void replicate_edges(float* buf, int rows, int v_firs
 // same kernel shape with coalesced, TMA-friendly rows).
 // grid = (ceil(Sw/64), ceil(Sh/OUT), ntiles*5), dynamic smem = (OUT + 2m) * 256 B
 // ------------------------------------------------------------------------------------------------
-template <int OUT>
+template <int OUT, bool FUSED>
 __global__ void __launch_bounds__(256) fb_blur_v_kernel(const __grid_constant__ CUtensorMap mapM, FbBatch b,
                                                         const __grid_constant__ FbConsts cst) {
     extern __shared__ __align__(128) float smem[];
@@ -359,7 +369,7 @@ __global__ void __launch_bounds__(256) fb_blur_v_kernel(const __grid_constant__ 
 #pragma unroll
     for (int grp = 0; grp < OUT / 64; ++grp) {
         int o0 = grp * 64 + warp * kR;
-        if (y0 + o0 < Sh) conv8x2(reinterpret_cast<const u64*>(smem) + (o0 + m) * kRowU + lane, m, cst.k2, nz, acc[grp]);
+        if (y0 + o0 < Sh) conv8x2<FUSED>(reinterpret_cast<const u64*>(smem) + (o0 + m) * kRowU + lane, m, cst.k2, nz, acc[grp]);
     }
     __syncthreads();  // everyone is done reading the inputs: reuse the buffer as the transpose stage
     constexpr int SP = OUT + 1;
@@ -394,6 +404,7 @@ __global__ void __launch_bounds__(256) fb_blur_v_kernel(const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------
 constexpr int kFlowPitch = 66;  // float2 per x-row of the flow stage (64 + 2: 16-byte aligned rows, few bank conflicts)
 
+template <bool FUSED>
 __global__ void __launch_bounds__(256, 2) fb_blur_h_kernel(const __grid_constant__ CUtensorMap mapVT, FbBatch b,
                                                             const __grid_constant__ FbConsts cst, int last_iter,
                                                             float2* __restrict__ flow_out) {
@@ -426,7 +437,7 @@ __global__ void __launch_bounds__(256, 2) fb_blur_h_kernel(const __grid_constant
     for (int c = 0; c < 5; ++c) {
         mbar_wait(&bars[c & 1], (c >> 1) & 1);
         replicate_edges(buf[c & 1], rows, x0 - m, Sw);
-        if (active) conv8x2(reinterpret_cast<const u64*>(buf[c & 1]) + (warp * kR + m) * kRowU + lane, m, cst.k2, nz, acc[c]);
+        if (active) conv8x2<FUSED>(reinterpret_cast<const u64*>(buf[c & 1]) + (warp * kR + m) * kRowU + lane, m, cst.k2, nz, acc[c]);
         __syncthreads();  // buffer c&1 is free again
         if (c + 2 < 5 && threadIdx.x == 0) {
             mbar_expect_tx(&bars[c & 1], box_bytes);
@@ -596,9 +607,10 @@ extern "C" size_t ma_farneback_workspace_bytes(int h, int w, int T, int ov, int 
     return (size_t)n_batch * kSlotPlanes * plane_floats(g) * sizeof(float);
 }
 
-extern "C" int ma_farneback_tiles(const void* mov, const void* ref, size_t pitch, int dtype, int h, int w,
-                                  int T, int ov, int win, int iters, int tile_begin, int tile_end,
-                                  float* flow_out, void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int ma_farneback_tiles_ex(const void* mov, const void* ref, size_t pitch, int dtype, int h, int w,
+                                     int T, int ov, int win, int iters, int tile_begin, int tile_end,
+                                     float* flow_out, void* workspace, size_t workspace_bytes, unsigned flags, void* stream) {
+    const bool fused = (flags & MA_FB_CONTRACT_FMA) != 0;
     if (!mov || !ref || !flow_out || !workspace || h <= 0 || w <= 0) return invalid("ma_farneback_tiles: bad argument");
     if (dtype != MA_U8 && dtype != MA_U16) return invalid("ma_farneback_tiles: dtype must be MA_U8 or MA_U16");
     if (iters < 1) return invalid("ma_farneback_tiles: iterations must be >= 1");
@@ -627,9 +639,12 @@ extern "C" int ma_farneback_tiles(const void* mov, const void* ref, size_t pitch
     const size_t h_smem = std::max((size_t)2 * (kStep + 2 * m) * kRowF * sizeof(float), (size_t)kStep * kFlowPitch * sizeof(float2));
     static bool attr_set = false;
     if (!attr_set) {
-        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 256));
-        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 256));
-        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 256));
+        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 256));
+        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 256));
+        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_h_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 256));
+        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 256));
+        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 256));
+        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_h_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 256));
         attr_set = true;
     }
     for (int t0 = tile_begin; t0 < tile_end; t0 += cap) {
@@ -654,11 +669,14 @@ extern "C" int ma_farneback_tiles(const void* mov, const void* ref, size_t pitch
         for (int it = 0; it < iters; ++it) {
             { KernelScope ks(K_BLUR_V, s, tpx);
             dim3 vg(ceil_div(g.Sw, kRowF), ceil_div(g.Sh, vout), b.ntiles * 5);
-            if (vout == 128) fb_blur_v_kernel<128><<<vg, 256, v_smem, s>>>(mapM, b, cst);
-            else fb_blur_v_kernel<64><<<vg, 256, v_smem, s>>>(mapM, b, cst); }
+            if (vout == 128 && !fused) fb_blur_v_kernel<128, false><<<vg, 256, v_smem, s>>>(mapM, b, cst);
+            else if (vout == 128) fb_blur_v_kernel<128, true><<<vg, 256, v_smem, s>>>(mapM, b, cst);
+            else if (!fused) fb_blur_v_kernel<64, false><<<vg, 256, v_smem, s>>>(mapM, b, cst);
+            else fb_blur_v_kernel<64, true><<<vg, 256, v_smem, s>>>(mapM, b, cst); }
             { KernelScope ks(K_BLUR_H, s, tpx);
-            fb_blur_h_kernel<<<dim3(ceil_div(g.Sh, kRowF), ceil_div(g.Sw, kStep), b.ntiles), 256, h_smem, s>>>(
-                mapVT, b, cst, it == iters - 1, (float2*)flow_out); }
+            dim3 hg(ceil_div(g.Sh, kRowF), ceil_div(g.Sw, kStep), b.ntiles);
+            if (!fused) fb_blur_h_kernel<false><<<hg, 256, h_smem, s>>>(mapVT, b, cst, it == iters - 1, (float2*)flow_out);
+            else fb_blur_h_kernel<true><<<hg, 256, h_smem, s>>>(mapVT, b, cst, it == iters - 1, (float2*)flow_out); }
             if (it < iters - 1) {
                 KernelScope ks(K_UPDATE0, s, tpx);
                 fb_update_kernel<<<dim3(ceil_div(g.Sw, 64), ceil_div(g.Sh, 4), b.ntiles), 256, 0, s>>>(b);
@@ -667,4 +685,11 @@ extern "C" int ma_farneback_tiles(const void* mov, const void* ref, size_t pitch
         MA_LAUNCH_CHECK("farneback kernels");
     }
     return MA_OK;
+}
+
+extern "C" int ma_farneback_tiles(const void* mov, const void* ref, size_t pitch, int dtype, int h, int w,
+                                  int T, int ov, int win, int iters, int tile_begin, int tile_end,
+                                  float* flow_out, void* workspace, size_t workspace_bytes, void* stream) {
+    return ma_farneback_tiles_ex(mov, ref, pitch, dtype, h, w, T, ov, win, iters, tile_begin, tile_end, flow_out, workspace,
+                                 workspace_bytes, 0u, stream);
 }

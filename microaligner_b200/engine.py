@@ -76,13 +76,15 @@ class LevelLayout:
 
 class Engine:
     def __init__(self, tile_size=1000, overlap=100, num_pyr_lvl=4, num_iterations=3, use_full_res_img=False,
-                 use_dog=False, comm: Optional[parallel.Comm] = None, log: Callable[[str], None] = None):
+                 use_dog=False, comm: Optional[parallel.Comm] = None, log: Callable[[str], None] = None,
+                 contract_fma: bool = False):
         self.T, self.ov = int(tile_size), int(overlap)
         self.num_pyr_lvl, self.iters = int(num_pyr_lvl), int(num_iterations)
         self.full_res, self.use_dog = bool(use_full_res_img), bool(use_dog)
         self.comm = comm or parallel.get()
         self.win = self.ov - (1 - self.ov % 2)         # optflow_registrator.py:91
         self._log = log
+        self.contract_fma = bool(contract_fma)   # opt-in fast window blur (not bit-identical to OpenCV)
         self.decisions: List[dict] = []
         self.gather_flow = True      # False: with several ranks the returned flow is valid on this rank's band only
         self.flow_layout = None
@@ -243,9 +245,10 @@ class Engine:
             this_flow = torch.empty((L.h, L.w, 2), dtype=torch.float32, device=ref.device)
             with self.phase("farneback" if L.tiled else "farneback(untiled level)"):
                 if L.tiled:
-                    ops.farneback_tiles(fb_mov, fb_ref, T, ov, self.win, self.iters, L.fb_tiles[L.rank], out=this_flow)
+                    ops.farneback_tiles(fb_mov, fb_ref, T, ov, self.win, self.iters, L.fb_tiles[L.rank], out=this_flow,
+                                        contract_fma=self.contract_fma)
                 else:
-                    ops.farneback_tiles(fb_mov, fb_ref, 0, 0, self.win, self.iters, out=this_flow)
+                    ops.farneback_tiles(fb_mov, fb_ref, 0, 0, self.win, self.iters, out=this_flow, contract_fma=self.contract_fma)
             del fb_mov, fb_ref
             if L.sharded:   # tile centres -> the row bands (+ overlap) the row-wise stages work on
                 with self.phase("exchange"):

@@ -166,8 +166,9 @@ def n_tiles(h: int, w: int, tile_size: int) -> int:
 
 
 def farneback_tiles(mov: torch.Tensor, ref: torch.Tensor, tile_size: int, overlap: int, win: int, iters: int,
-                    tile_range=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Stitched flow of the tiled (tile_size > 0) or untiled (tile_size <= 0) Farneback."""
+                    tile_range=None, out: Optional[torch.Tensor] = None, contract_fma: bool = False) -> torch.Tensor:
+    """Stitched flow of the tiled (tile_size > 0) or untiled (tile_size <= 0) Farneback.
+    contract_fma=True trades bit parity for speed in the window blur (MA_FB_CONTRACT_FMA)."""
     _req(mov, "moving image")
     _req(ref, "reference image")
     if mov.shape != ref.shape or mov.dtype != ref.dtype:
@@ -183,9 +184,9 @@ def farneback_tiles(mov: torch.Tensor, ref: torch.Tensor, tile_size: int, overla
     nb = max(1, min(t1 - t0, FARNEBACK_WORKSPACE_BUDGET // slot))
     ws = _fb_workspace(ref.device, nb * slot)
     es = ref.element_size()
-    check(lib.ma_farneback_tiles(mov.data_ptr(), ref.data_ptr(), w * es, _code(ref), h, w, T, int(overlap), int(win),
-                                 int(iters), int(t0), int(t1), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
-          "ma_farneback_tiles")
+    check(lib.ma_farneback_tiles_ex(mov.data_ptr(), ref.data_ptr(), w * es, _code(ref), h, w, T, int(overlap), int(win),
+                                    int(iters), int(t0), int(t1), out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                    1 if contract_fma else 0, _stream()), "ma_farneback_tiles")
     return out
 
 

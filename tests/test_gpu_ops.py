@@ -159,3 +159,15 @@ def test_minmax(ops):
     img = rng.integers(5, 60000, (300, 401)).astype(np.uint16)
     mm = ops.minmax(dev(img)).cpu().numpy()
     assert mm[0] == img.min() and mm[1] == img.max()
+
+
+def test_farneback_contract_fma_within_contract(ops):
+    """Opt-in FMA-contracted window blur: not bit-identical, but far inside the 0.01 / 0.1 px contract per call."""
+    ref, mov = synth_pair(520, 610, 3, np.uint16)
+    want = rf.calc_flow(ref, mov, 250, 40, 39, 3, rf.NpBackend())
+    exact = ops.farneback_tiles(dev(mov), dev(ref), 250, 40, 39, 3).cpu().numpy()
+    fast = ops.farneback_tiles(dev(mov), dev(ref), 250, 40, 39, 3, contract_fma=True).cpu().numpy()
+    assert np.array_equal(exact, want)
+    epe = np.sqrt(((fast - want) ** 2).sum(-1))
+    assert epe.mean() <= 1e-4 and epe.max() <= 1e-3, (epe.mean(), epe.max())
+    assert not np.array_equal(fast, want)   # it really is the other arithmetic
