@@ -73,14 +73,6 @@ constexpr int PE_BW = 64, PE_BH = 16;
 constexpr int PE_RW = PE_BW + 4, PE_RH = PE_BH + 4;   // raw window
 constexpr int PE_PW = PE_BW + 2, PE_PH = PE_BH + 2;   // prefiltered window (1-px halo for the expansion)
 
-template <typename T>
-__device__ __forceinline__ float window_px(const T* __restrict__ img, size_t pitch, const TileGeom& g,
-                                           int oy, int ox, int ty, int tx) {
-    int gy = oy + ty, gx = ox + tx;  // zero padding outside the image
-    if ((unsigned)gy >= (unsigned)g.h || (unsigned)gx >= (unsigned)g.w) return 0.0f;
-    return (float)__ldg((const T*)((const char*)img + (size_t)gy * pitch) + gx);
-}
-
 __device__ __forceinline__ float border_w(int d) {
     // {0.14, 0.14, 0.4472, 0.4472, 0.4472}
     return d < 2 ? 0.14f : 0.4472f;
