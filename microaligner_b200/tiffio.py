@@ -1,0 +1,350 @@
+"""Minimal uncompressed (Big)TIFF page I/O for the registration pipeline.
+
+The reference reads pages with ``tifffile.TiffFile(p).series[0].pages[i].asarray()``
+(shared_modules/utils.py:69-72) and writes the registered stack into ``tifffile.memmap(path, shape=(1, C, Z, Y, X),
+dtype, bigtiff=True, description=ome_xml, contiguous=True)`` (__main__.py:116-132).  tifffile is not part of this
+environment, and at GPU speed the pipeline is I/O bound, so this module provides exactly that surface, pure
+Python + numpy, for the only pixel layout the pipeline produces and that a B200 can be fed at line rate:
+
+* classic TIFF ("II*\\0" / "MM\\0*") and BigTIFF ("II+\\0"), any byte order;
+* single-sample, unsigned 8 / 16 bit (or 32-bit float) pages, Compression = 1 (none), strips only;
+* pages whose strips are contiguous in the file are returned as zero-copy ``np.memmap`` views
+  (``TiffPage.asarray()``), or read straight into a caller-supplied, page-locked array (``read_into``) so the next
+  H2D copy is a single DMA transfer;
+* ``memmap(path, shape, dtype, description)`` creates a contiguous multi-page BigTIFF and returns the pixel block
+  as one writeable ``np.memmap`` of the requested shape -- the reference's output idiom.
+
+Anything else (compression, tiles, multiple samples, sub-IFDs) raises ``TiffFormatError`` rather than guessing."""
+import mmap
+import os
+import struct
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+# tag ids
+IMAGE_WIDTH, IMAGE_LENGTH, BITS_PER_SAMPLE, COMPRESSION, PHOTOMETRIC = 256, 257, 258, 259, 262
+IMAGE_DESCRIPTION, STRIP_OFFSETS, SAMPLES_PER_PIXEL, ROWS_PER_STRIP, STRIP_BYTE_COUNTS = 270, 273, 277, 278, 279
+PLANAR_CONFIG, SOFTWARE, SAMPLE_FORMAT, TILE_WIDTH = 284, 305, 339, 322
+
+_TYPE_SIZES = {1: 1, 2: 1, 3: 2, 4: 4, 5: 8, 6: 1, 7: 1, 8: 2, 9: 4, 10: 8, 11: 4, 12: 8, 16: 8, 17: 8, 18: 8}
+_TYPE_FMT = {1: "B", 2: "c", 3: "H", 4: "I", 6: "b", 7: "B", 8: "h", 9: "i", 11: "f", 12: "d", 16: "Q", 17: "q", 18: "Q"}
+
+
+class TiffFormatError(ValueError):
+    pass
+
+
+class TiffPage:
+    def __init__(self, tif: "TiffFile", tags: Dict[int, tuple]):
+        self._tif = tif
+        self.tags = tags
+        self.width = int(tags[IMAGE_WIDTH][0])
+        self.height = int(tags[IMAGE_LENGTH][0])
+        bits = int(tags.get(BITS_PER_SAMPLE, (1,))[0])
+        spp = int(tags.get(SAMPLES_PER_PIXEL, (1,))[0])
+        fmt = int(tags.get(SAMPLE_FORMAT, (1,))[0])
+        comp = int(tags.get(COMPRESSION, (1,))[0])
+        if comp != 1:
+            raise TiffFormatError(f"compressed TIFF (Compression={comp}) is not supported")
+        if spp != 1:
+            raise TiffFormatError(f"SamplesPerPixel={spp}: only single-channel pages are supported")
+        if TILE_WIDTH in tags:
+            raise TiffFormatError("tiled TIFF is not supported (strips only)")
+        kinds = {(8, 1): "u1", (16, 1): "u2", (32, 1): "u4", (32, 3): "f4", (16, 2): "i2", (8, 2): "i1"}
+        if (bits, fmt) not in kinds:
+            raise TiffFormatError(f"unsupported sample type: {bits} bits, SampleFormat {fmt}")
+        self.dtype = np.dtype(tif.byteorder + kinds[(bits, fmt)]) if bits > 8 else np.dtype(kinds[(bits, fmt)])
+        self.shape = (self.height, self.width)
+        self.offsets = [int(v) for v in tags[STRIP_OFFSETS]]
+        self.counts = [int(v) for v in tags[STRIP_BYTE_COUNTS]]
+        self.nbytes = self.height * self.width * self.dtype.itemsize
+        if sum(self.counts) != self.nbytes:
+            raise TiffFormatError("strip byte counts do not add up to an uncompressed page")
+        self.is_contiguous = all(self.offsets[i] + self.counts[i] == self.offsets[i + 1] for i in range(len(self.offsets) - 1))
+
+    @property
+    def description(self) -> Optional[str]:
+        v = self.tags.get(IMAGE_DESCRIPTION)
+        return v[0] if v else None
+
+    def asarray(self) -> np.ndarray:
+        """The page as a (height, width) array in native byte order; zero-copy memmap view when possible."""
+        if self.is_contiguous:
+            a = np.ndarray(self.shape, self.dtype, buffer=self._tif._map, offset=self.offsets[0])
+        else:
+            buf = bytearray(self.nbytes)
+            self._read_strips(memoryview(buf))
+            a = np.frombuffer(buf, self.dtype).reshape(self.shape)
+        if not a.dtype.isnative:
+            a = a.astype(a.dtype.newbyteorder("="))
+        return a
+
+    def read_into(self, out: np.ndarray) -> np.ndarray:
+        """Fill a caller-owned (e.g. page-locked) array of the page's shape and dtype."""
+        if out.shape != self.shape or out.dtype.itemsize != self.dtype.itemsize or not out.flags.c_contiguous:
+            raise ValueError(f"read_into needs a C-contiguous array of shape {self.shape} and item size {self.dtype.itemsize}")
+        self._read_strips(memoryview(out.reshape(-1).view(np.uint8)))
+        if not self.dtype.isnative:
+            out.byteswap(inplace=True)
+        return out
+
+    def _read_strips(self, dst: memoryview):
+        pos = 0
+        for off, n in zip(self.offsets, self.counts):
+            dst[pos:pos + n] = self._tif._map[off:off + n]
+            pos += n
+
+
+class TiffSeries:
+    def __init__(self, pages: List[TiffPage], shape: Tuple[int, ...], axes: str):
+        self.pages, self.shape, self.axes = pages, shape, axes
+        self.dtype = pages[0].dtype.newbyteorder("=") if pages else None
+
+
+class TiffFile:
+    """``with TiffFile(path) as tif: tif.series[0].pages[i].asarray()`` -- the reference's read idiom."""
+
+    def __init__(self, path):
+        self.path = os.fspath(path)
+        self._fh = open(self.path, "rb")
+        self._map = mmap.mmap(self._fh.fileno(), 0, access=mmap.ACCESS_READ)
+        head = self._map[:16]
+        if head[:2] == b"II":
+            self.byteorder = "<"
+        elif head[:2] == b"MM":
+            self.byteorder = ">"
+        else:
+            raise TiffFormatError("not a TIFF file")
+        magic = struct.unpack(self.byteorder + "H", head[2:4])[0]
+        if magic == 42:
+            self.bigtiff = False
+            first = struct.unpack(self.byteorder + "I", head[4:8])[0]
+        elif magic == 43:
+            self.bigtiff = True
+            if struct.unpack(self.byteorder + "HH", head[4:8]) != (8, 0):
+                raise TiffFormatError("malformed BigTIFF header")
+            first = struct.unpack(self.byteorder + "Q", head[8:16])[0]
+        else:
+            raise TiffFormatError(f"unknown TIFF magic {magic}")
+        self.pages = self._read_ifds(first)
+        self.series = [self._make_series()]
+
+    # -- parsing --------------------------------------------------------------------------------
+    def _read_ifds(self, offset: int) -> List[TiffPage]:
+        bo, big = self.byteorder, self.bigtiff
+        pages, seen = [], set()
+        while offset:
+            if offset in seen:
+                raise TiffFormatError("IFD loop")
+            seen.add(offset)
+            if big:
+                n = struct.unpack(bo + "Q", self._map[offset:offset + 8])[0]
+                pos, esz = offset + 8, 20
+            else:
+                n = struct.unpack(bo + "H", self._map[offset:offset + 2])[0]
+                pos, esz = offset + 2, 12
+            tags = {}
+            for i in range(n):
+                e = self._map[pos + i * esz:pos + (i + 1) * esz]
+                tag, typ = struct.unpack(bo + "HH", e[:4])
+                cnt = struct.unpack(bo + ("Q" if big else "I"), e[4:12] if big else e[4:8])[0]
+                val = e[12:20] if big else e[8:12]
+                size = _TYPE_SIZES.get(typ)
+                if size is None:
+                    continue
+                nbytes = size * cnt
+                if nbytes > len(val):
+                    ptr = struct.unpack(bo + ("Q" if big else "I"), val)[0]
+                    raw = self._map[ptr:ptr + nbytes]
+                else:
+                    raw = val[:nbytes]
+                if typ == 2:
+                    tags[tag] = (raw.rstrip(b"\x00").decode("utf-8", "replace"),)
+                elif typ in (5, 10):
+                    f = "I" if typ == 5 else "i"
+                    v = struct.unpack(bo + f * (2 * cnt), raw)
+                    tags[tag] = tuple(v[2 * k] / v[2 * k + 1] if v[2 * k + 1] else 0.0 for k in range(cnt))
+                else:
+                    tags[tag] = struct.unpack(bo + _TYPE_FMT[typ] * cnt, raw)
+            nxt = pos + n * esz
+            offset = struct.unpack(bo + ("Q" if big else "I"), self._map[nxt:nxt + (8 if big else 4)])[0]
+            pages.append(TiffPage(self, tags))
+        return pages
+
+    def _make_series(self) -> TiffSeries:
+        p0 = self.pages[0]
+        same = all(p.shape == p0.shape and p.dtype == p0.dtype for p in self.pages)
+        shape = ((len(self.pages),) + p0.shape) if (same and len(self.pages) > 1) else p0.shape
+        desc = self.ome_metadata
+        axes = "YX" if len(shape) == 2 else "IYX"
+        if desc and same:
+            dims = _ome_dims(desc)
+            if dims and dims[0] * dims[1] * dims[2] == len(self.pages):
+                t, c, z = dims
+                shape, axes = tuple(v for v in (t, c, z) if True) + p0.shape, "TCZYX"
+                # the reference requires 4-D CZYX inputs (img_checks.py:50-65): drop a singleton T
+                if t == 1:
+                    shape, axes = shape[1:], "CZYX"
+        return TiffSeries(self.pages, shape, axes)
+
+    @property
+    def ome_metadata(self) -> Optional[str]:
+        d = self.pages[0].description if self.pages else None
+        return d if d and "OME" in d[:400] else None
+
+    def asarray(self) -> np.ndarray:
+        s = self.series[0]
+        return np.stack([p.asarray() for p in s.pages]).reshape(s.shape) if len(s.pages) > 1 else s.pages[0].asarray()
+
+    def close(self):
+        try:
+            self._map.close()
+        finally:
+            self._fh.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+def _ome_dims(xml: str) -> Optional[Tuple[int, int, int]]:
+    """(SizeT, SizeC, SizeZ) of the first Pixels element of an OME-XML string, if present."""
+    import re
+    m = re.search(r"<Pixels\b[^>]*>", xml)
+    if not m:
+        return None
+    out = []
+    for k in ("SizeT", "SizeC", "SizeZ"):
+        mm = re.search(k + r'="(\d+)"', m.group(0))
+        if not mm:
+            return None
+        out.append(int(mm.group(1)))
+    return tuple(out)
+
+
+# ------------------------------------------------------------------------------------- writing
+def _ifd_entry(tag, typ, count, value) -> bytes:
+    """BigTIFF IFD entry with an inline (<= 8 byte) value or an offset."""
+    return struct.pack("<HHQ", tag, typ, count) + value.ljust(8, b"\x00")
+
+
+def memmap(path, shape: Sequence[int], dtype, description: Optional[str] = None, software: str = "microaligner_b200"):
+    """Create a little-endian BigTIFF holding prod(shape[:-2]) contiguous uncompressed pages of shape[-2:] and return
+    the pixel block as a writeable np.memmap of `shape` (tifffile.memmap(..., bigtiff=True, contiguous=True))."""
+    dtype = np.dtype(dtype).newbyteorder("<")
+    if dtype.kind not in "uf" or dtype.itemsize not in (1, 2, 4):
+        raise TiffFormatError(f"unsupported dtype {dtype}")
+    shape = tuple(int(s) for s in shape)
+    if len(shape) < 2:
+        raise ValueError("shape needs at least (Y, X)")
+    h, w = shape[-2:]
+    npages = int(np.prod(shape[:-2])) if len(shape) > 2 else 1
+    page_bytes = h * w * dtype.itemsize
+    desc = (description or "").encode("utf-8") + b"\x00"
+    soft = software.encode() + b"\x00"
+    # layout: header (16) | description | software | IFDs | pad to 4096 | pixel block
+    pos = 16
+    desc_off, pos = pos, pos + len(desc)
+    soft_off, pos = pos, pos + len(soft)
+    pos = (pos + 7) // 8 * 8
+    n_tags = 12
+    ifd_size = 8 + n_tags * 20 + 8
+    ifd0 = pos
+    data_off = (ifd0 + npages * ifd_size + 4095) // 4096 * 4096
+    with open(os.fspath(path), "wb") as f:
+        f.write(struct.pack("<2sHHHQ", b"II", 43, 8, 0, ifd0))
+        f.write(desc)
+        f.write(soft)
+        f.write(b"\x00" * (ifd0 - f.tell()))
+        sample_format = 3 if dtype.kind == "f" else 1
+        for i in range(npages):
+            entries = [
+                _ifd_entry(IMAGE_WIDTH, 4, 1, struct.pack("<I", w)),
+                _ifd_entry(IMAGE_LENGTH, 4, 1, struct.pack("<I", h)),
+                _ifd_entry(BITS_PER_SAMPLE, 3, 1, struct.pack("<H", dtype.itemsize * 8)),
+                _ifd_entry(COMPRESSION, 3, 1, struct.pack("<H", 1)),
+                _ifd_entry(PHOTOMETRIC, 3, 1, struct.pack("<H", 1)),
+                _ifd_entry(IMAGE_DESCRIPTION, 2, len(desc), struct.pack("<Q", desc_off) if len(desc) > 8 else desc),
+                _ifd_entry(STRIP_OFFSETS, 16, 1, struct.pack("<Q", data_off + i * page_bytes)),
+                _ifd_entry(SAMPLES_PER_PIXEL, 3, 1, struct.pack("<H", 1)),
+                _ifd_entry(ROWS_PER_STRIP, 4, 1, struct.pack("<I", h)),
+                _ifd_entry(STRIP_BYTE_COUNTS, 16, 1, struct.pack("<Q", page_bytes)),
+                _ifd_entry(SOFTWARE, 2, len(soft), struct.pack("<Q", soft_off) if len(soft) > 8 else soft),
+                _ifd_entry(SAMPLE_FORMAT, 3, 1, struct.pack("<H", sample_format)),
+            ]
+            assert len(entries) == n_tags
+            nxt = ifd0 + (i + 1) * ifd_size if i + 1 < npages else 0
+            f.write(struct.pack("<Q", n_tags) + b"".join(entries) + struct.pack("<Q", nxt))
+        f.write(b"\x00" * (data_off - f.tell()))
+        f.truncate(data_off + npages * page_bytes)
+    return np.memmap(os.fspath(path), dtype=dtype, mode="r+", offset=data_off, shape=shape)
+
+
+def imwrite(path, data: np.ndarray, description: Optional[str] = None):
+    mm = memmap(path, data.shape, data.dtype, description)
+    mm[...] = data
+    mm.flush()
+    del mm
+
+
+# ------------------------------------------------------------------------------------- pipeline glue
+class TiffPageProvider:
+    """cycle -> channel -> z -> callable returning the page in a page-locked staging buffer, for
+    pipeline.register_and_save_ofreg_imgs.  `layout[cycle][channel][z] = (path, page index)`."""
+
+    def __init__(self, layout: Dict[int, Dict[str, Dict[int, Tuple[str, int]]]], pinned: bool = True, n_buffers: int = 3):
+        self.layout = layout
+        self._files: Dict[str, TiffFile] = {}
+        self._pinned = pinned
+        self._bufs: List[np.ndarray] = []
+        self._next = 0
+        self._n = n_buffers
+
+    def _file(self, path) -> TiffFile:
+        if path not in self._files:
+            self._files[path] = TiffFile(path)
+        return self._files[path]
+
+    def _staging(self, shape, dtype) -> np.ndarray:
+        if not self._pinned:
+            return np.empty(shape, dtype)
+        if len(self._bufs) < self._n or self._bufs[0].shape != shape or self._bufs[0].dtype != dtype:
+            import torch
+            self._bufs = [torch.empty(shape, dtype=torch.from_numpy(np.empty(0, dtype)).dtype, pin_memory=True).numpy()
+                          for _ in range(self._n)]
+        b = self._bufs[self._next % self._n]
+        self._next += 1
+        return b
+
+    def page(self, path, index) -> np.ndarray:
+        p = self._file(path).pages[index]
+        return p.read_into(self._staging(p.shape, p.dtype.newbyteorder("=")))
+
+    def dataset(self):
+        return {cyc: {ch: {z: (lambda pi=pi: self.page(*pi)) for z, pi in zs.items()} for ch, zs in chs.items()}
+                for cyc, chs in self.layout.items()}
+
+    def close(self):
+        for f in self._files.values():
+            f.close()
+        self._files.clear()
+
+
+class TiffStackSink:
+    """sink(cycle, channel, z, image) writing into one contiguous BigTIFF stack (1, C_total, Z, Y, X) --
+    the reference's SaveOutputToCycleStack layout (__main__.py:372-398)."""
+
+    def __init__(self, path, channel_index: Dict[Tuple[int, str], int], n_z: int, yx: Tuple[int, int], dtype,
+                 description: Optional[str] = None):
+        self.index = channel_index
+        self.mm = memmap(path, (1, len(channel_index), n_z) + tuple(yx), dtype, description)
+
+    def __call__(self, cyc, ch, z, image: np.ndarray):
+        self.mm[0, self.index[(cyc, ch)], z] = image
+
+    def close(self):
+        self.mm.flush()
+        del self.mm

@@ -71,3 +71,33 @@ def test_max_projection(cuda):
     want = rf.max_project(pages, rf.CvBackend())
     assert np.array_equal(pipeline.max_project_pages(pages).cpu().numpy(), want)
     assert np.array_equal(rf.max_project(pages, rf.NpBackend()), want)
+
+
+def test_pipeline_from_tiff_files(cuda, tmp_path):
+    """C4 in miniature: per-cycle CZYX BigTIFF inputs -> registered (1, C_total, Z, Y, X) BigTIFF stack, pages staged
+    through page-locked buffers; compared with the oracle run on the same arrays."""
+    import yaml
+    from microaligner_b200 import pipeline, tiffio
+    cfg = yaml.safe_load(YAML)
+    params = pipeline.optflow_parameters(cfg)
+    ds = make_dataset(h=380, w=460, cycles=3, channels=("DAPI", "CD3"), nz=2)
+    layout, index = {}, {}
+    for c, chans in ds.items():
+        stack = np.stack([np.stack([chans[ch][z] for z in sorted(chans[ch])]) for ch in chans])   # C, Z, Y, X
+        path = tmp_path / f"cycle{c}.tif"
+        tiffio.imwrite(path, stack)
+        layout[c] = {ch: {z: (str(path), ci * 2 + z) for z in range(2)} for ci, ch in enumerate(chans)}
+        for ci, ch in enumerate(chans):
+            index[(c, ch)] = (c - 1) * 2 + ci
+    prov = tiffio.TiffPageProvider(layout)
+    sink = tiffio.TiffStackSink(tmp_path / "registered.tif", index, 2, (380, 460), np.uint16, description="registered")
+    with contextlib.redirect_stdout(io.StringIO()):
+        pipeline.run_opt_flow_reg(cfg, prov.dataset(), sink)
+    sink.close()
+    prov.close()
+    want = rf.register_cycles(ds, "DAPI", be=rf.CvBackend(), **params)
+    with tiffio.TiffFile(tmp_path / "registered.tif") as tif:
+        got = tif.asarray().reshape(6, 2, 380, 460)
+    for (c, ch), ci in index.items():
+        for z in range(2):
+            assert np.array_equal(got[ci, z], want[(c, ch, z)]), (c, ch, z)
