@@ -35,8 +35,10 @@ PARAMS = dict(num_pyr_lvl=4, num_iterations=3, tile_size=1000, overlap=100, use_
 
 # algorithmic HBM bytes per unit (unit = tile-pixel for fb_*, pixel otherwise; u16 input)
 ALG_BYTES = {
-    "fb_polyexp": 44.0, "fb_update0": 60.0, "fb_blur_v": 20.0,
-    "fb_blur_h": None,  # 68 per non-final iteration (R0 20 + R1 20 + M 20 + flow 8), 8 on the final one
+    "fb_polyexp": 64.0,   # 2 x (2 in + 20 out) + fused first UpdateMatrices (M 20 out; its R0/R1 inputs stay on chip)
+    "fb_blur_v": 20.0,    # M in (the transposed V it writes is an intermediate of the blur+solve stage)
+    "fb_blur_h": 8.0,     # flow out
+    "fb_update": 68.0,    # flow 8 + R0 20 + R1 20 + M 20
     "warp_tiles": 12.0, "tile_max": 16.0, "merge_tiles": 24.0, "pyrdown": 2.5, "pyrup_flow": 10.0,
     "minmax": 2.0, "dog_row": 2.0, "dog_col": 4.0, "dog_quant": 5.0, "nmi_hist": 2.0,
 }
@@ -296,19 +298,17 @@ def run_b200(args):
     if dom:
         k = kernels[dom]
         bpu = ALG_BYTES.get(dom)
-        if dom == "fb_blur_h":
-            bpu = (68.0 * (N - 1) + 8.0) / N
         avg_ms = k["ms_per_step"] / k["launches_per_step"]
         units_per_launch = k["units_per_step"] / k["launches_per_step"]
         achieved = (bpu or 0) * units_per_launch / (avg_ms * 1e-3) / 1e9
-        roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        roofline = {"kernel": dom, "bound": "hbm", "actual_bound": "fp32 pipe" if dom in FP32_INSTR else "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "peak_source": peak_src, "alg_bytes_per_unit": bpu, "units_per_launch": units_per_launch,
                     "avg_launch_ms": avg_ms, "share_of_step": k["ms_per_step"] / ms_dev,
                     "traffic": (NCU_TRAFFIC_PER_UNIT[dom] * units_per_launch) if dom in NCU_TRAFFIC_PER_UNIT else None}
         if dom in FP32_INSTR and clocks.get("sm_mhz"):
             fp_peak = 148 * 128 * clocks["sm_mhz"] * 1e6
             fp_ach = FP32_INSTR[dom] * units_per_launch / (avg_ms * 1e-3)
-            roofline["fp32_issue"] = {"note": "kernel is FP32-issue bound, not HBM bound (DESIGN.md)", "achieved_ginstr_s": fp_ach / 1e9,
+            roofline["fp32_issue"] = {"note": "kernel is FP32-pipe bound, not HBM bound (DESIGN.md section 4): separately rounded FP32 lane-ops vs 148 SM x 128 lanes x clock", "achieved_ginstr_s": fp_ach / 1e9,
                                       "peak_ginstr_s": fp_peak / 1e9, "frac": fp_ach / fp_peak, "at_sm_mhz": clocks["sm_mhz"]}
     line = {
         "metric": "Mpixel/s registered (Farneback flow + warp)", "value": value, "unit": "Mpx/s", "n_gpus": world,

@@ -78,6 +78,11 @@ int ma_merge_flows_tiles(const float* f1, const float* f2, int h, int w, int T, 
 int ma_merge_flows_tile_rows(const float* f1, const float* f2, int h, int w, int T, int ov, float* out,
                              void* workspace, int tile_row_begin, int tile_row_end, void* stream);
 
+/* ---- opt-in, NOT reference behaviour: proper composition of two flows in image
+ * coordinates, out(p) = f2(p) + bilinear(f1, p - f2(p)), rows [row_begin, row_end). */
+int ma_compose_flows_rows(const float* f1, const float* f2, int h, int w, float* out,
+                          int row_begin, int row_end, void* stream);
+
 /* ---- tiled Farneback: TileFlowCalc.calc_flow / farneback (optflow_reg/flow_calc.py:30-98) =
  * cv.calcOpticalFlowFarneback(mov, ref, None, 0.5, 0, win, iters, 1, 1.7, FARNEBACK_GAUSSIAN)
  * on every tile window in [tile_begin, tile_end) (row-major tile index), centres stitched into

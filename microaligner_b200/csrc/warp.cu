@@ -160,9 +160,50 @@ __global__ void __launch_bounds__(256) merge_tiles_kernel(const float2* __restri
     out[idx] = r;
 }
 
+// ---- opt-in "corrected" composition (NOT the reference's behaviour): the flow that warps
+// by f1 first and by f2 second is  m(p) = f2(p) + f1(p - f2(p)), sampled in IMAGE coordinates (no tile windows),
+// same 1/32-px fixed-point bilinear scheme, zero outside the image.
+__global__ void __launch_bounds__(256) compose_flows_kernel(const float2* __restrict__ f1, const float2* __restrict__ f2,
+                                                            int h, int w, float2* __restrict__ out, int ybeg, int yend) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = ybeg + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= yend) return;
+    size_t idx = (size_t)y * w + x;
+    float2 b = __ldg(&f2[idx]);
+    int sx = cv_round_x32(__fsub_rn((float)x, b.x)), sy = cv_round_x32(__fsub_rn((float)y, b.y));
+    int ix = sx >> 5, iy = sy >> 5, ax = sx & 31, ay = sy & 31;
+    auto tap = [&](int yy, int xx) -> float2 {
+        bool ok = (unsigned)xx < (unsigned)w && (unsigned)yy < (unsigned)h;
+        return ok ? __ldg(&f1[(size_t)yy * w + xx]) : make_float2(0.f, 0.f);
+    };
+    float2 v00 = tap(iy, ix), v01 = tap(iy, ix + 1), v10 = tap(iy + 1, ix), v11 = tap(iy + 1, ix + 1);
+    float fx = __fmul_rn((float)ax, 0.03125f), fy = __fmul_rn((float)ay, 0.03125f);
+    float ux = __fsub_rn(1.0f, fx), uy = __fsub_rn(1.0f, fy);
+    float w00 = __fmul_rn(uy, ux), w01 = __fmul_rn(uy, fx), w10 = __fmul_rn(fy, ux), w11 = __fmul_rn(fy, fx);
+    float qx = __fmul_rn(v00.x, w00), qy = __fmul_rn(v00.y, w00);
+    qx = __fadd_rn(qx, __fmul_rn(v01.x, w01)); qy = __fadd_rn(qy, __fmul_rn(v01.y, w01));
+    qx = __fadd_rn(qx, __fmul_rn(v10.x, w10)); qy = __fadd_rn(qy, __fmul_rn(v10.y, w10));
+    qx = __fadd_rn(qx, __fmul_rn(v11.x, w11)); qy = __fadd_rn(qy, __fmul_rn(v11.y, w11));
+    out[idx] = make_float2(__fadd_rn(b.x, qx), __fadd_rn(b.y, qy));
+}
+
 }  // namespace ma
 
 using namespace ma;
+
+extern "C" int ma_compose_flows_rows(const float* f1, const float* f2, int h, int w, float* out,
+                                     int row_begin, int row_end, void* stream) {
+    if (!f1 || !f2 || !out || h <= 0 || w <= 0) return invalid("ma_compose_flows_rows: bad argument");
+    if (h > 32767 * 2 || w > 32767 * 2) return invalid("ma_compose_flows_rows: image too large for 1/32-px fixed point");
+    if (row_begin < 0 || row_end > h || row_begin > row_end) return invalid("ma_compose_flows_rows: bad row range");
+    if (row_begin == row_end) return MA_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    dim3 block(64, 4), grid(ceil_div(w, 64), ceil_div(row_end - row_begin, 4));
+    KernelScope ks(K_MERGE, s, (double)(row_end - row_begin) * w);
+    compose_flows_kernel<<<grid, block, 0, s>>>((const float2*)f1, (const float2*)f2, h, w, (float2*)out, row_begin, row_end);
+    MA_LAUNCH_CHECK("compose_flows_kernel");
+    return MA_OK;
+}
 
 extern "C" int ma_warp_tiles_rows(const void* img, size_t img_pitch, int dtype, const float* flow, int h, int w,
                                   int T, int ov, void* out, size_t out_pitch, int row_begin, int row_end, void* stream) {

@@ -77,7 +77,7 @@ class LevelLayout:
 class Engine:
     def __init__(self, tile_size=1000, overlap=100, num_pyr_lvl=4, num_iterations=3, use_full_res_img=False,
                  use_dog=False, comm: Optional[parallel.Comm] = None, log: Callable[[str], None] = None,
-                 contract_fma: bool = False):
+                 contract_fma: bool = False, corrected: bool = False):
         self.T, self.ov = int(tile_size), int(overlap)
         self.num_pyr_lvl, self.iters = int(num_pyr_lvl), int(num_iterations)
         self.full_res, self.use_dog = bool(use_full_res_img), bool(use_dog)
@@ -85,6 +85,9 @@ class Engine:
         self.win = self.ov - (1 - self.ov % 2)         # optflow_registrator.py:91
         self._log = log
         self.contract_fma = bool(contract_fma)   # opt-in fast window blur (not bit-identical to OpenCV)
+        # opt-in, NOT the reference's behaviour: compose flows properly (m = f2 + f1(p - f2)) and scale the final
+        # up-sampling by 2 -- removes quirks Q1 / Q2 that keep the reference's multi-level flow far from ground truth
+        self.corrected = bool(corrected)
         self.decisions: List[dict] = []
         self.gather_flow = True      # False: with several ranks the returned flow is valid on this rank's band only
         self.flow_layout = None
@@ -281,12 +284,12 @@ class Engine:
                     else:
                         m_flow, m_layout = self._upscale_to_full(this_flow, L, full, factor)
                 elif lvl == num_lvl - 1:
-                    merged = ops.merge_flows_tile_rows(m_flow, this_flow, T, ov, L.tile_rows[L.rank], torch.empty_like(this_flow))
+                    merged = self._merge(m_flow, this_flow, L)
                     m_flow, m_layout = merged, L
                     if not self.full_res:
                         m_flow, m_layout = self._upscale_to_full(merged, L, full, factor)
                 else:
-                    merged = ops.merge_flows_tile_rows(m_flow, this_flow, T, ov, L.tile_rows[L.rank], torch.empty_like(this_flow))
+                    merged = self._merge(m_flow, this_flow, L)
                     m_flow, m_layout = self.pyr_up(merged, L, Ln, 2.0), Ln
             else:
                 self.log("    Worse alignment than before")
@@ -311,6 +314,14 @@ class Engine:
                 comm.gather_rows(m_flow, m_layout.bands)
         return m_flow
 
+    def _merge(self, m_flow: torch.Tensor, this_flow: torch.Tensor, L: LevelLayout) -> torch.Tensor:
+        out = torch.empty_like(this_flow)
+        if not self.corrected:   # merge_two_flows per tile (optflow_registrator.py:37-47, 217-240), quirks included
+            return ops.merge_flows_tile_rows(m_flow, this_flow, self.T, self.ov, L.tile_rows[L.rank], out)
+        if L.sharded:            # p - f2(p) may leave the band: the opt-in mode simply gathers the accumulated flow
+            self.comm.gather_rows(m_flow, L.bands)
+        return ops.compose_flows_rows(m_flow, this_flow, L.band, out)
+
     def _upscale_to_full(self, flow: torch.Tensor, L: LevelLayout, full: LevelLayout, factor: int):
         """_upscale_flow_to_full_res (optflow_registrator.py:204-215): NOT scaled by 2 (quirk Q2)."""
         if abs(flow.shape[0] - full.h) <= 1:
@@ -319,7 +330,7 @@ class Engine:
         out, lay = flow, L
         for i in range(num_lvls):
             if i == num_lvls - 1:
-                out, lay = self.pyr_up(flow, L, full, 1.0), full
+                out, lay = self.pyr_up(flow, L, full, 2.0 if self.corrected else 1.0), full
             else:  # unreachable for contiguous factors; kept for parity with the reference's loop
                 mid = LevelLayout(2 * flow.shape[0], 2 * flow.shape[1], self.T, self.ov, self.comm)
                 out, lay = self.pyr_up(flow, L, mid, 1.0), mid

@@ -263,6 +263,14 @@ def merge_flows_tile_rows(f1, f2, tile_size, overlap, tile_rows, out):
     return out
 
 
+def compose_flows_rows(f1, f2, rows, out):
+    """Opt-in corrected composition: out(p) = f2(p) + bilinear(f1, p - f2(p)) for image rows [rows)."""
+    h, w, _ = f1.shape
+    check(lib.ma_compose_flows_rows(f1.data_ptr(), f2.data_ptr(), h, w, out.data_ptr(), int(rows[0]), int(rows[1]), _stream()),
+          "ma_compose_flows_rows")
+    return out
+
+
 def minmax_rows(img, rows, out=None):
     """[min, max] (float32 device tensor) of image rows [rows[0], rows[1])."""
     h, w = img.shape

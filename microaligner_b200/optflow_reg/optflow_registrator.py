@@ -44,6 +44,10 @@ class OptFlowRegistrator:
         # flow is bit-identical to the reference's.  False: FMA-contracted blur, ~1.5x faster in the two dominant
         # kernels, each Farneback call within ~1e-6 px of the exact one (inside the 0.01 / 0.1 px contract)
         self.exact_arithmetic = True
+        # False (default) reproduces the reference including its quirks.  True: flows of successive levels are
+        # composed properly (m = f2 + f1(p - f2) in image coordinates) and the final up-sampling is scaled by 2 --
+        # NOT what the reference computes, but much closer to the true displacement
+        self.corrected_composition = False
 
     @property
     def ref_img(self):
@@ -150,7 +154,8 @@ class OptFlowRegistrator:
         mov = ops.to_device(self._mov_img, ref.device)
         self._full_shape = tuple(ref.shape)
         eng = Engine(self.tile_size, self.overlap, self.num_pyr_lvl, self.num_iterations, self.use_full_res_img,
-                     self.use_dog, comm=parallel.get(), contract_fma=not self.exact_arithmetic)
+                     self.use_dog, comm=parallel.get(), contract_fma=not self.exact_arithmetic,
+                     corrected=self.corrected_composition)
         eng.gather_flow = self.gather_flow or host_result
         m_flow = eng.register(ref, mov)     # the coarse-to-fine loop, sharded over the ranks of parallel.get()
         self.decisions = eng.decisions

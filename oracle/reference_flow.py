@@ -218,8 +218,17 @@ def image_pyramid(arr, num_pyr_lvl, use_full_res_img, be):
     return pyr, factors
 
 
+def compose_flows(f1, f2, be):
+    """Opt-in 'corrected' composition used by microaligner_b200 (NOT the reference): f2 + f1(p - f2) in image coordinates."""
+    h, w = f1.shape[:2]
+    m = np.negative(f2)
+    m[:, :, 0] += np.arange(w)
+    m[:, :, 1] += np.arange(h).reshape(-1, 1)
+    return f2 + be.remap(f1, m)
+
+
 def register(ref_img, mov_img, num_pyr_lvl=4, num_iterations=3, tile_size=1000, overlap=100,
-             use_full_res_img=False, use_dog=False, be=None, log=None, force_decisions=None):
+             use_full_res_img=False, use_dog=False, be=None, log=None, force_decisions=None, corrected=False):
     """OptFlowRegistrator.register (optflow_registrator.py:93-173).  `log` (a list) receives one
     dict per level: factor, mi_after, mi_before, better.  `force_decisions` overrides the gate
     (test hook used to exercise the 'Worse' branches)."""
@@ -237,7 +246,7 @@ def register(ref_img, mov_img, num_pyr_lvl=4, num_iterations=3, tile_size=1000, 
         out = flow
         n = int(log2(factor))
         for i in range(n):
-            out = be.pyr_up(flow, full_hw, 1) if i == n - 1 else be.pyr_up(flow, (2 * flow.shape[0], 2 * flow.shape[1]), 1)
+            out = be.pyr_up(flow, full_hw, 2 if corrected else 1) if i == n - 1 else be.pyr_up(flow, (2 * flow.shape[0], 2 * flow.shape[1]), 1)
         return out
 
     ref_pyr, factors = image_pyramid(ref_img, num_pyr_lvl, use_full_res_img, be)
@@ -263,11 +272,12 @@ def register(ref_img, mov_img, num_pyr_lvl=4, num_iterations=3, tile_size=1000, 
             if lvl == 0:
                 m_flow = be.pyr_up(this_flow, nxt, 2) if num_lvl > 1 else upscale_to_full(this_flow, factor)
             elif lvl == num_lvl - 1:
-                m_flow = merge_flows_tiled(m_flow, this_flow, T, ov, be)
+                m_flow = compose_flows(m_flow, this_flow, be) if corrected else merge_flows_tiled(m_flow, this_flow, T, ov, be)
                 if not use_full_res_img:
                     m_flow = upscale_to_full(m_flow, factor)
             else:
-                m_flow = be.pyr_up(merge_flows_tiled(m_flow, this_flow, T, ov, be), nxt, 2)
+                merged = compose_flows(m_flow, this_flow, be) if corrected else merge_flows_tiled(m_flow, this_flow, T, ov, be)
+                m_flow = be.pyr_up(merged, nxt, 2)
         else:
             if lvl == 0:
                 shape = nxt if num_lvl > 1 else mov_img.shape
