@@ -45,7 +45,9 @@ ALG_BYTES = {
 # FP32 lane-instructions per unit of the two FP32-bound kernels: 5 planes x (1 + 3 m), m = 49
 FP32_INSTR = {"fb_blur_v": 5 * (1 + 3 * 49), "fb_blur_h": 5 * (1 + 3 * 49)}
 # dram__bytes_read.sum + dram__bytes_write.sum per unit from the committed ncu --set full capture (profiles/)
-NCU_TRAFFIC_PER_UNIT = {}
+NCU_TRAFFIC_PER_UNIT = {  # profiles/r01_ncu_farneback_full.txt: (dram_rd + dram_wr) / 51.84 M tile-px per launch
+    "fb_blur_h": 27.85, "fb_blur_v": 39.43, "fb_polyexp": 62.58, "fb_update": 68.08,
+}
 
 
 def measured_hbm_peak():
