@@ -62,6 +62,8 @@ __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigne
     return r;
 }
 
+// NOTE: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into ONE FFMA2, so this kernel really issues FADD2 + FFMA2
+// (2 packed instructions for 3 "operations") -- kept to document that.
 __global__ void k_packed_addmul(float* out, float a, float b) {
     unsigned long long acc[NACC / 2], A = pk(a, a), B = pk(b, b);
 #pragma unroll
@@ -71,6 +73,27 @@ __global__ void k_packed_addmul(float* out, float a, float b) {
         for (int j = 0; j < NACC / 2; ++j) {
             unsigned long long t = add2(acc[j], A);
             acc[j] = add2(acc[j], mul2(t, B));
+        }
+    }
+    unsigned long long s = acc[0];
+#pragma unroll
+    for (int j = 1; j < NACC / 2; ++j) s = add2(s, acc[j]);
+    float x, y;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(s));
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x + y;
+}
+
+// separately rounded add, mul, add with the multiply written as fma(t, B, -0) whose -0 is a runtime value:
+// three packed instructions (FADD2, FFMA2, FADD2) -- the sequence the bit-exact blur kernels use
+__global__ void k_packed_addmul_unfused(float* out, float a, float nzf) {
+    unsigned long long acc[NACC / 2], A = pk(a, a), B = pk(0.9999f, 0.9999f), NZ = pk(nzf, nzf);
+#pragma unroll
+    for (int j = 0; j < NACC / 2; ++j) acc[j] = pk(threadIdx.x + j, threadIdx.x - j);
+    for (int i = 0; i < ITERS; ++i) {
+#pragma unroll
+        for (int j = 0; j < NACC / 2; ++j) {
+            unsigned long long t = add2(acc[j], A);
+            acc[j] = add2(acc[j], fma2(t, B, NZ));
         }
     }
     unsigned long long s = acc[0];
@@ -102,20 +125,20 @@ __global__ void k_packed_fma(float* out, float a, float b) {
 }
 
 template <typename K>
-void run(const char* name, K kern, float* out, double lane_ops_per_thread) {
+void run(const char* name, K kern, float* out, double lane_ops_per_thread, float arg2 = 0.9999f) {
     int blocks = 148 * 8, threads = 256;
-    kern<<<blocks, threads>>>(out, 1.0001f, 0.9999f);
+    kern<<<blocks, threads>>>(out, 1.0001f, arg2);
     cudaDeviceSynchronize();
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
     cudaEventRecord(a);
-    for (int r = 0; r < 5; ++r) kern<<<blocks, threads>>>(out, 1.0001f, 0.9999f);
+    for (int r = 0; r < 5; ++r) kern<<<blocks, threads>>>(out, 1.0001f, arg2);
     cudaEventRecord(b);
     cudaEventSynchronize(b);
     float ms;
     cudaEventElapsedTime(&ms, a, b);
     double ops = 5.0 * blocks * threads * lane_ops_per_thread;
-    printf("%-22s %8.3f ms  %8.2f T lane-op/s  (%s)\n", name, ms / 5, ops / (ms * 1e-3) / 1e12, cudaGetErrorString(cudaGetLastError()));
+    printf("%-58s %8.3f ms  %8.2f T lane-op/s  (%s)\n", name, ms / 5, ops / (ms * 1e-3) / 1e12, cudaGetErrorString(cudaGetLastError()));
 }
 
 int main() {
@@ -124,7 +147,8 @@ int main() {
     double per_thread = (double)ITERS * NACC * 3;  // float results produced per thread
     run("scalar add,mul,add", k_scalar_addmul, out, per_thread);
     run("scalar fma x3", k_scalar_fma, out, per_thread);
-    run("packed add,mul,add x2", k_packed_addmul, out, per_thread);
+    run("packed add,mul,add (contracted to FADD2+FFMA2 by ptxas)", k_packed_addmul, out, per_thread);
+    run("packed add,mul,add unfused (FADD2,FFMA2,FADD2)", k_packed_addmul_unfused, out, per_thread, -0.0f);
     run("packed fma x3 x2", k_packed_fma, out, per_thread);
     int clk;
     cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
