@@ -132,6 +132,43 @@ def warp_tiles(img: torch.Tensor, flow: torch.Tensor, tile_size: int, overlap: i
     return out
 
 
+def warp_tiles_host_streamed(image: np.ndarray, flow: torch.Tensor, tile_size: int, overlap: int) -> np.ndarray:
+    """Warper.warp for a HOST image and a device-resident flow: the image goes up, is warped and comes back one
+    tile row at a time on three streams, so the H2D and D2H transfers overlap (PCIe is full duplex) instead of
+    running back to back.  Same kernel, same rows, same result as warp_tiles."""
+    a = np.ascontiguousarray(image)
+    if a.dtype not in (np.uint8, np.uint16):
+        raise TypeError(f"unsupported image dtype {a.dtype}; expected uint8 or uint16")
+    h, w = a.shape
+    T, ov = int(tile_size), int(overlap)
+    dev = flow.device
+    src = torch.from_numpy(a)
+    img_d = torch.empty((h, w), dtype=src.dtype, device=dev)
+    out_d = torch.empty_like(img_d)
+    out_h = torch.empty((h, w), dtype=src.dtype, pin_memory=True)
+    cur = torch.cuda.current_stream()
+    up, comp, down = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    for s in (up, comp, down):
+        s.wait_stream(cur)          # the flow (and the allocations) were produced on the current stream
+    uploaded = 0
+    for y0 in range(0, h, T):
+        y1 = min(y0 + T, h)
+        need = min(y1 + ov, h)      # a tile row reads image rows [y0 - ov, y1 + ov)
+        if need > uploaded:
+            with torch.cuda.stream(up):
+                img_d[uploaded:need].copy_(src[uploaded:need], non_blocking=True)
+            uploaded = need
+        comp.wait_stream(up)
+        with torch.cuda.stream(comp):
+            warp_tiles_rows(img_d, flow, T, ov, (y0, y1), out_d)
+        down.wait_stream(comp)
+        with torch.cuda.stream(down):
+            out_h[y0:y1].copy_(out_d[y0:y1], non_blocking=True)
+    down.synchronize()
+    cur.wait_stream(comp)
+    return out_h.numpy()
+
+
 def merge_flows_tiles(f1: torch.Tensor, f2: torch.Tensor, tile_size: int, overlap: int) -> torch.Tensor:
     _req(f1, "flow1")
     _req(f2, "flow2")

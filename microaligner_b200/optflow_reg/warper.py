@@ -23,6 +23,14 @@ class Warper:
 
     def warp(self):
         host_result = not isinstance(self.image, torch.Tensor)
+        if host_result and parallel.get().world == 1 and isinstance(self.image, np.ndarray) and self.image.ndim == 2 \
+                and self.image.dtype in (np.uint8, np.uint16) and self.image.shape[0] >= 2 * self.tile_size:
+            # large host image, single GPU: stream tile rows up / through the kernel / down on three streams
+            flow = ops.to_device(self.flow)
+            image, self.image, self.flow = self.image, np.array([]), np.array([])
+            if tuple(flow.shape) != image.shape + (2,) or flow.dtype != torch.float32:
+                raise ValueError(f"flow must be float32 of shape {image.shape + (2,)}, got {flow.dtype} {tuple(flow.shape)}")
+            return ops.warp_tiles_host_streamed(image, flow, self.tile_size, self.overlap)
         img = ops.to_device(self.image, self.flow.device if isinstance(self.flow, torch.Tensor) else None)
         flow = ops.to_device(self.flow, img.device)
         self.image = np.array([])
