@@ -89,6 +89,7 @@ class Engine:
         # up-sampling by 2 -- removes quirks Q1 / Q2 that keep the reference's multi-level flow far from ground truth
         self.corrected = bool(corrected)
         self.decisions: List[dict] = []
+        self.force_decisions = None  # test hook (list of bools per level), mirrors oracle.reference_flow.register
         self.gather_flow = True      # False: with several ranks the returned flow is valid on this rank's band only
         self.flow_layout = None
 
@@ -271,6 +272,8 @@ class Engine:
             del ref_dog, wd, od
             self.log("    MI score after:", after, "| MI score before:", before)
             better = after > before
+            if self.force_decisions is not None:      # test hook: exercise the "Worse alignment" branches
+                better = bool(self.force_decisions[lvl])
             self.decisions.append(dict(factor=factor, mi_after=after, mi_before=before, better=better))
             Ln = layouts[lvl + 1] if lvl + 1 < num_lvl else None
 

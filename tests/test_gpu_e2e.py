@@ -159,3 +159,21 @@ def test_corrected_composition_opt_in(cuda):
         assert np.array_equal(got, want)
         results[full_res] = epe(got)
     assert results[False] < 0.1 and results[True] < 0.1          # the reference-faithful mode sits at 0.56 - 1.5 px here
+
+
+@pytest.mark.parametrize("decisions", [(False, False, False), (True, False, True), (True, True, False), (False, True, False)])
+@pytest.mark.parametrize("full_res", [False, True])
+def test_forced_worse_branches(cuda, decisions, full_res):
+    """Every branch of the reference's better / worse logic (optflow_registrator.py:134-169), including the x4
+    mid-level and the last-level 'Worse' paths, forced identically in the engine and in the oracle."""
+    from microaligner_b200 import ops
+    from microaligner_b200.engine import Engine
+    ref, mov = synth_pair(620, 760, 5, np.uint16)
+    kw = dict(num_pyr_lvl=2, num_iterations=1, tile_size=150, overlap=20, use_full_res_img=full_res)
+    dec = decisions if full_res else decisions[:2]
+    want = rf.register(ref, mov, be=rf.CvBackend(), force_decisions=dec, **kw)
+    eng = Engine(**kw)
+    eng.force_decisions = dec
+    with contextlib.redirect_stdout(io.StringIO()):
+        got = eng.register(ops.to_device(ref), ops.to_device(mov)).cpu().numpy()
+    assert got.shape == want.shape and np.array_equal(got, want)
