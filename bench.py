@@ -358,8 +358,11 @@ def main():
     ap.add_argument("--strong", action="store_true", help="keep the 20000^2 pair at every GPU count (strong scaling)")
     ap.add_argument("--cpu-sample", type=int, default=4000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--use-dog", action="store_true", help="BASELINE configs[2]: same pair with the DoG prefilter enabled")
     ap.add_argument("--trace", action="store_true", help="extra untimed step with per-phase synchronised wall times (stderr)")
     args = ap.parse_args()
+    if args.use_dog:
+        PARAMS["use_dog"] = True
     args.scaling = "weak"
     if args.size is None:
         n = max(1, int(os.environ.get("WORLD_SIZE", args.gpus)))

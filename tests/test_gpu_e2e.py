@@ -177,3 +177,25 @@ def test_forced_worse_branches(cuda, decisions, full_res):
     with contextlib.redirect_stdout(io.StringIO()):
         got = eng.register(ops.to_device(ref), ops.to_device(mov)).cpu().numpy()
     assert got.shape == want.shape and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(use_full_res_img=True, use_dog=True)])
+def test_baseline_config_c1_2048(cuda, kw):
+    """BASELINE.json configs[0]: 2048 x 2048 uint16 pair with known sinusoidal displacement, default parameters
+    (and the full-resolution + DoG variant) -- bit-identical flow and warped image vs the CPU path."""
+    from microaligner_b200 import OptFlowRegistrator, Warper
+    ref, mov = synth_pair(2048, 2048, 0, np.uint16)
+    log = []
+    want = rf.register(ref, mov, be=rf.CvBackend(workers=8), log=log, **kw)
+    want_img = rf.warp(mov, want, 1000, 100, rf.CvBackend())
+    reg = OptFlowRegistrator()
+    for k, v in kw.items():
+        setattr(reg, k, v)
+    reg.ref_img, reg.mov_img = ref, mov
+    with contextlib.redirect_stdout(io.StringIO()):
+        flow = reg.register()
+    assert [d["better"] for d in reg.decisions] == [l["better"] for l in log]
+    assert np.array_equal(flow, want)
+    w = Warper()
+    w.image, w.flow = mov, flow
+    assert np.array_equal(w.warp(), want_img)
