@@ -199,3 +199,32 @@ def test_baseline_config_c1_2048(cuda, kw):
     w = Warper()
     w.image, w.flow = mov, flow
     assert np.array_equal(w.warp(), want_img)
+
+
+def test_microscopy_like_blobs_with_dog(cuda):
+    """Second input distribution: sparse Gaussian blobs on a dark background + Poisson noise, DoG on,
+    full resolution, ragged size -- exercises zero-ish tiles, the per-tile max()==0 merge branches and MI near-ties."""
+    import cv2
+    from microaligner_b200 import OptFlowRegistrator, Warper
+    from tests.util import blobs
+    h, w = 2300, 3100
+    ref = blobs(h, w, 11, np.uint16)
+    ref[:700, :900] = 0                                   # a dead corner: all-zero tiles at every level
+    y, x = np.mgrid[0:h, 0:w].astype(np.float32)
+    mov = cv2.remap(ref, x + 2.5 * np.sin(2 * np.pi * y / 700), y + 1.5 * np.cos(2 * np.pi * x / 900), cv2.INTER_LINEAR)
+    kw = dict(num_pyr_lvl=3, use_full_res_img=True, use_dog=True)
+    log = []
+    want = rf.register(ref, mov, be=rf.CvBackend(workers=8), log=log, **kw)
+    reg = OptFlowRegistrator()
+    for k, v in kw.items():
+        setattr(reg, k, v)
+    reg.ref_img, reg.mov_img = ref, mov
+    with contextlib.redirect_stdout(io.StringIO()):
+        flow = reg.register()
+    assert [d["better"] for d in reg.decisions] == [l["better"] for l in log]
+    epe = np.sqrt(((flow - want) ** 2).sum(-1))
+    assert epe.mean() <= 0.01 and epe.max() <= 0.1
+    assert np.array_equal(flow, want)
+    w_ = Warper()
+    w_.image, w_.flow = mov, flow
+    assert np.array_equal(w_.warp(), rf.warp(mov, want, 1000, 100, rf.CvBackend()))
