@@ -35,39 +35,55 @@ __global__ void __launch_bounds__(256) pyrdown_kernel(const T* __restrict__ src,
 __device__ __forceinline__ float2 mul2(float2 a, float s) { return make_float2(__fmul_rn(a.x, s), __fmul_rn(a.y, s)); }
 __device__ __forceinline__ float2 add2(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
 
-// horizontally up-sampled value (unscaled, weights sum to 8) of source row `row` at output column dx
-__device__ __forceinline__ float2 up_row(const float2* __restrict__ row, int n, int dx, float scale) {
-    auto S = [&](int i) { return mul2(__ldg(row + i), scale); };
-    int i = dx >> 1;
-    if (n == 1) return mul2(S(0), 8.0f);
-    if (dx & 1) {
-        if (i == n - 1) return mul2(S(n - 1), 8.0f);
-        return mul2(add2(S(i), S(i + 1)), 4.0f);
+// One thread produces the 2 x 2 output block (rows 2r, 2r+1; columns 2c, 2c+1) from the 3 x 3 source
+// neighbourhood: 9 float2 loads for 4 outputs.  Horizontal pass per source row (unscaled, weights sum to 8):
+//   even column 2c : interior (s[c-1] + 6 s[c]) + s[c+1];  c == 0: 6 s[0] + 2 s[1];  c == n-1: s[n-2] + 7 s[n-1]
+//   odd column 2c+1: interior (s[c] + s[c+1]) * 4;         c == n-1: 8 s[n-1];       n == 1: 8 s[0] for both
+__device__ __forceinline__ void up_row_pair(const float2* __restrict__ row, int n, int c, float scale, float2& even, float2& odd) {
+    float2 sc = mul2(__ldg(row + c), scale);
+    if (n == 1) {
+        even = odd = mul2(sc, 8.0f);
+        return;
     }
-    if (i == 0) return add2(mul2(S(0), 6.0f), mul2(S(1), 2.0f));
-    if (i == n - 1) return add2(S(n - 2), mul2(S(n - 1), 7.0f));
-    return add2(add2(S(i - 1), mul2(S(i), 6.0f)), S(i + 1));
+    if (c == n - 1) {
+        float2 sl = mul2(__ldg(row + c - 1), scale);
+        even = add2(sl, mul2(sc, 7.0f));
+        odd = mul2(sc, 8.0f);
+        return;
+    }
+    float2 sr = mul2(__ldg(row + c + 1), scale);
+    odd = mul2(add2(sc, sr), 4.0f);
+    if (c == 0) {
+        even = add2(mul2(sc, 6.0f), mul2(sr, 2.0f));
+    } else {
+        float2 sl = mul2(__ldg(row + c - 1), scale);
+        even = add2(add2(sl, mul2(sc, 6.0f)), sr);
+    }
 }
 
 __global__ void __launch_bounds__(256) pyrup_flow_kernel(const float2* __restrict__ src, int h, int w,
                                                          float2* __restrict__ dst, int dh, int dw, float scale,
                                                          int ybeg, int yend) {
-    int dx = blockIdx.x * blockDim.x + threadIdx.x;
-    int dy = ybeg + blockIdx.y * blockDim.y + threadIdx.y;
-    if (dx >= dw || dy >= yend) return;
-    int i = dy >> 1;
-    int i2 = min(i + 1, h - 1);
-    float2 r1 = up_row(src + (size_t)i * w, w, dx, scale);
-    float2 r2 = up_row(src + (size_t)i2 * w, w, dx, scale);
-    float2 o;
-    if (dy & 1) {
-        o = mul2(mul2(add2(r1, r2), 4.0f), 0.015625f);
-    } else {
-        int i0 = h > 1 ? reflect101(i - 1, h) : 0;
-        float2 r0 = up_row(src + (size_t)i0 * w, w, dx, scale);
-        o = mul2(add2(add2(r0, mul2(r1, 6.0f)), r2), 0.015625f);
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;                  // source column
+    const int r = (ybeg >> 1) + blockIdx.y * blockDim.y + threadIdx.y;    // source row
+    if (c >= w || r >= h || 2 * r >= yend) return;
+    const int r0 = h > 1 ? reflect101(r - 1, h) : 0, r2 = min(r + 1, h - 1);
+    float2 e0, o0, e1, o1, e2, o2;
+    up_row_pair(src + (size_t)r0 * w, w, c, scale, e0, o0);
+    up_row_pair(src + (size_t)r * w, w, c, scale, e1, o1);
+    up_row_pair(src + (size_t)r2 * w, w, c, scale, e2, o2);
+    const int dy = 2 * r, dx = 2 * c;
+    const bool has_odd_col = dx + 1 < dw;
+    if (dy >= ybeg) {   // even output row: (r0 + 6 r1) + r2, generic 3-row form (top reflect-101, bottom replicate)
+        float2* out = dst + (size_t)dy * dw + dx;
+        out[0] = mul2(add2(add2(e0, mul2(e1, 6.0f)), e2), 0.015625f);
+        if (has_odd_col) out[1] = mul2(add2(add2(o0, mul2(o1, 6.0f)), o2), 0.015625f);
     }
-    dst[(size_t)dy * dw + dx] = o;
+    if (dy + 1 < yend && dy + 1 < dh) {   // odd output row: (r1 + r2) * 4
+        float2* out = dst + (size_t)(dy + 1) * dw + dx;
+        out[0] = mul2(mul2(add2(e1, e2), 4.0f), 0.015625f);
+        if (has_odd_col) out[1] = mul2(mul2(add2(o1, o2), 4.0f), 0.015625f);
+    }
 }
 
 }  // namespace ma
@@ -106,7 +122,8 @@ extern "C" int ma_pyrup_flow_rows(const float* src, int h, int w, float* dst, in
         return invalid("ma_pyrup_flow: dstsize must be 2n or 2n-1 per axis");
     if (row_begin < 0 || row_end > dh || row_begin > row_end) return invalid("ma_pyrup_flow: bad row range");
     if (row_begin == row_end) return MA_OK;
-    dim3 block(32, 8), grid(ceil_div(dw, 32), ceil_div(row_end - row_begin, 8));
+    const int src_rows = ((row_end + 1) >> 1) - (row_begin >> 1);   // source rows whose 2-row output block touches the range
+    dim3 block(32, 8), grid(ceil_div(w, 32), ceil_div(src_rows, 8));
     KernelScope ks(K_PYRUP, (cudaStream_t)stream, (double)(row_end - row_begin) * dw);
     pyrup_flow_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const float2*)src, h, w, (float2*)dst, dh, dw, scale, row_begin, row_end);
     MA_LAUNCH_CHECK("pyrup_flow_kernel");
