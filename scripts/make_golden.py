@@ -95,6 +95,23 @@ def main():
     np.savez_compressed(os.path.join(OUT, "e2e_small.npz"), ref=ref, mov=mov, flow=flow.astype(np.float32), warped=warped,
                         stdout=buf.getvalue(), num_pyr_lvl=1, num_iterations=2, tile_size=150, overlap=20,
                         use_full_res_img=True, use_dog=True, **v)
+    # 7. the rarely taken 'Worse alignment' branches, forced in the unmodified reference (gate monkeypatched)
+    ref, mov = synth_pair(360, 440, 10, np.uint16)
+    forced = {}
+    for name, dec, full_res in (("tft_full", (True, False, True), True), ("ft_nofull", (False, True), False), ("tf_nofull", (True, False), False)):
+        it = iter(dec)
+        old = ofr.check_if_higher_similarity
+        ofr.check_if_higher_similarity = lambda *a, **k: [next(it)]
+        try:
+            r = mod.OptFlowRegistrator()
+            r.num_pyr_lvl, r.num_iterations, r.tile_size, r.overlap, r.use_full_res_img = 2, 1, 120, 16, full_res
+            r.ref_img, r.mov_img = ref, mov
+            with contextlib.redirect_stdout(io.StringIO()):
+                forced[name] = r.register()
+        finally:
+            ofr.check_if_higher_similarity = old
+    np.savez_compressed(os.path.join(OUT, "forced_decisions.npz"), ref=ref, mov=mov, num_pyr_lvl=2, num_iterations=1,
+                        tile_size=120, overlap=16, **forced, **v)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
 

@@ -228,3 +228,40 @@ def test_microscopy_like_blobs_with_dog(cuda):
     w_ = Warper()
     w_.image, w_.flow = mov, flow
     assert np.array_equal(w_.warp(), rf.warp(mov, want, 1000, 100, rf.CvBackend()))
+
+
+@pytest.mark.parametrize("name,dec,full_res", [("tft_full", (True, False, True), True), ("ft_nofull", (False, True), False),
+                                               ("tf_nofull", (True, False), False)])
+def test_golden_forced_decisions_from_reference(cuda, name, dec, full_res):
+    """Flows produced by the UNMODIFIED reference with its gate forced (tests/golden/forced_decisions.npz)."""
+    import os
+    from microaligner_b200 import ops
+    from microaligner_b200.engine import Engine
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "forced_decisions.npz"))
+    eng = Engine(tile_size=int(g["tile_size"]), overlap=int(g["overlap"]), num_pyr_lvl=int(g["num_pyr_lvl"]),
+                 num_iterations=int(g["num_iterations"]), use_full_res_img=full_res)
+    eng.force_decisions = list(dec)
+    with contextlib.redirect_stdout(io.StringIO()):
+        got = eng.register(ops.to_device(g["ref"]), ops.to_device(g["mov"])).cpu().numpy()
+    assert np.array_equal(got, g[name])
+
+
+def test_golden_e2e_from_reference(cuda):
+    """register() + warp() of the unmodified reference, frozen in tests/golden/e2e_small.npz."""
+    import os
+    from microaligner_b200 import OptFlowRegistrator, Warper
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "e2e_small.npz"))
+    reg = OptFlowRegistrator()
+    reg.num_pyr_lvl, reg.num_iterations = int(g["num_pyr_lvl"]), int(g["num_iterations"])
+    reg.tile_size, reg.overlap = int(g["tile_size"]), int(g["overlap"])
+    reg.use_full_res_img, reg.use_dog = bool(g["use_full_res_img"]), bool(g["use_dog"])
+    reg.ref_img, reg.mov_img = g["ref"], g["mov"]
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        flow = reg.register()
+    assert np.array_equal(flow, g["flow"])
+    assert buf.getvalue() == str(g["stdout"])          # the printed lines (MI scores included) are identical
+    w = Warper()
+    w.tile_size, w.overlap = reg.tile_size, reg.overlap
+    w.image, w.flow = g["mov"], flow
+    assert np.array_equal(w.warp(), g["warped"])

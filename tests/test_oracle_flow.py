@@ -43,3 +43,27 @@ def test_register_matches_reference(case):
         assert np.array_equal(f0, f1) and np.array_equal(w0, w1)
         better = [l.strip().startswith("Better") for l in out.splitlines() if "alignment than before" in l]
         assert better == [l["better"] for l in log]
+
+
+@pytest.mark.parametrize("decisions", [(False, False, False), (True, False, True), (False, True, False), (True, True, False)])
+@pytest.mark.parametrize("full_res", [False, True])
+def test_forced_decisions_match_reference(monkeypatch, decisions, full_res):
+    """The 'Worse alignment' branches (zeros at level 0, x4 at mid levels, x2 / pass-through at the last level,
+    optflow_registrator.py:151-169) are rare on real data: force the gate's verdicts in the unmodified reference
+    and in the oracle and compare bit for bit."""
+    mod = ref_shim.load()
+    import importlib
+    ofr = importlib.import_module("microaligner.optflow_reg.optflow_registrator")
+    ref, mov = synth_pair(520, 640, 3, np.uint16)
+    kw = dict(num_pyr_lvl=2, num_iterations=1, tile_size=150, overlap=20, use_full_res_img=full_res)
+    dec = list(decisions if full_res else decisions[:2])
+    it = iter(dec)
+    monkeypatch.setattr(ofr, "check_if_higher_similarity", lambda *a, **k: [next(it)])
+    r = mod.OptFlowRegistrator()
+    for k, v in kw.items():
+        setattr(r, k, v)
+    r.ref_img, r.mov_img = ref, mov
+    with contextlib.redirect_stdout(io.StringIO()):
+        want = r.register()
+    got = rf.register(ref, mov, be=rf.CvBackend(), force_decisions=dec, **kw)
+    assert want.shape == got.shape and np.array_equal(want, got)

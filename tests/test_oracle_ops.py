@@ -145,3 +145,15 @@ def test_split_stitch_roundtrip(shape):
     assert np.array_equal(rf.stitch(tiles, shape[0], shape[1], 1000, 100), a)
     f = rng.standard_normal(shape + (2,)).astype(np.float32)
     assert np.array_equal(rf.stitch(rf.split(f, 1000, 100), shape[0], shape[1], 1000, 100), f)
+
+
+FORCED = [("tft_full", (True, False, True), True), ("ft_nofull", (False, True), False), ("tf_nofull", (True, False), False)]
+
+
+@pytest.mark.parametrize("name,dec,full_res", FORCED)
+def test_golden_forced_decisions(name, dec, full_res):
+    g = gold("forced_decisions.npz")
+    kw = dict(num_pyr_lvl=int(g["num_pyr_lvl"]), num_iterations=int(g["num_iterations"]), tile_size=int(g["tile_size"]),
+              overlap=int(g["overlap"]), use_full_res_img=full_res)
+    got = rf.register(g["ref"], g["mov"], be=rf.CvBackend(), force_decisions=list(dec), **kw)
+    assert np.array_equal(got, g[name])
