@@ -428,10 +428,12 @@ extern "C" int ma_dog_diff_rows(const void* src, size_t src_pitch, int dtype, in
             set_error("ma_dog_diff_rows: cuTensorMapEncodeTiled failed");
             return MA_ERR_CUDA;
         }
-        static bool attr_set = false;
-        if (!attr_set) {
+        static bool attr_set[64] = {false};  // per device
+        int dev_id = 0;
+        cudaGetDevice(&dev_id);
+        if (dev_id < 0 || dev_id >= 64 || !attr_set[dev_id]) {
             MA_CUDA_CHECK(cudaFuncSetAttribute(dog_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * DC_ROWS * 64 * 4));
-            attr_set = true;
+            if (dev_id >= 0 && dev_id < 64) attr_set[dev_id] = true;
         }
         dog_col_kernel<<<dim3(ceil_div(w, 64), ceil_div(row_end - row_begin, DC_OUT)), 256, 2 * DC_ROWS * 64 * 4, s>>>(
             mapA, wp, h, w, diff, keys, taps, row_begin, row_end, ra); }

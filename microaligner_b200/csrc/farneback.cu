@@ -629,15 +629,17 @@ extern "C" int ma_farneback_tiles_ex(const void* mov, const void* ref, size_t pi
     const int vout = (m <= 49) ? 128 : 64;  // V-pass rows per CTA: box rows vout + 2m must stay <= 256
     const size_t v_smem = std::max((size_t)(vout + 2 * m) * kRowF * sizeof(float), (size_t)kRowF * (vout + 1) * sizeof(float));
     const size_t h_smem = std::max((size_t)2 * (kStep + 2 * m) * kRowF * sizeof(float), (size_t)kStep * kFlowPitch * sizeof(float2));
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};  // per device
+    int dev_id = 0;
+    cudaGetDevice(&dev_id);
+    if (dev_id < 0 || dev_id >= 64 || !attr_set[dev_id]) {
         MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 256));
         MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 256));
         MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_h_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 256));
         MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 256));
         MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 256));
         MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_h_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 256));
-        attr_set = true;
+        if (dev_id >= 0 && dev_id < 64) attr_set[dev_id] = true;
     }
     for (int t0 = tile_begin; t0 < tile_end; t0 += cap) {
         FbBatch b;

@@ -9,7 +9,7 @@ from oracle import reference_flow as rf
 from tests.util import random_flow
 
 pytestmark = pytest.mark.gpu
-SET = dict(deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+SET = dict(deadline=None, derandomize=True, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
 
 
 def dev(a):

@@ -1,0 +1,44 @@
+"""CPU: row-band / tile-range layout of the sharded engine (microaligner_b200.engine.LevelLayout)."""
+import pytest
+
+from microaligner_b200 import parallel
+from microaligner_b200.engine import LevelLayout
+
+
+class FakeComm:
+    def __init__(self, rank, world):
+        self.rank, self.world = rank, world
+
+    def tile_row_bands(self, ny):
+        return parallel.split_even(ny, self.world)
+
+
+@pytest.mark.parametrize("h,w,T,ov,world", [(20000, 20000, 1000, 100, 8), (2500, 2500, 1000, 100, 8), (5000, 5300, 1000, 100, 4),
+                                            (700, 820, 150, 20, 5), (1250, 1250, 1000, 100, 8)])
+def test_level_layout(h, w, T, ov, world):
+    layouts = [LevelLayout(h, w, T, ov, FakeComm(r, world)) for r in range(world)]
+    L = layouts[0]
+    assert L.tiled == (not max(h, w) / T < 2)
+    if not L.tiled:
+        assert not L.sharded and L.bands == [(0, h)] * world and L.fb_tiles == [(0, L.ny * L.nx)] * world
+        return
+    # bands partition the rows on tile-row boundaries; Farneback tiles are balanced to within one tile
+    assert L.bands[0][0] == 0 and L.bands[-1][1] <= h and max(b for _, b in L.bands) == h
+    for (a0, a1), (b0, b1) in zip(L.bands, L.bands[1:]):
+        assert a1 == b0 or b1 == b0            # contiguous (trailing bands may be empty)
+    assert all(a % T == 0 for a, b in L.bands if b > a)
+    sizes = [b - a for a, b in L.fb_tiles]
+    assert sum(sizes) == L.ny * L.nx and max(sizes) - min(sizes) <= 1
+    # the rows a rank's Farneback tiles read cover the windows of all its tiles
+    for r, (t0, t1) in enumerate(L.fb_tiles):
+        rows = L.fb_window_rows()[r]
+        for t in range(t0, t1):
+            i = t // L.nx
+            assert rows[0] <= max(i * T - ov, 0) and rows[1] >= min((i + 1) * T + ov, h)
+    # grow() clips to the image and leaves empty bands empty
+    for (a, b), (ga, gb) in zip(L.bands, L.grow(ov, ov + 7)):
+        if b > a:
+            assert ga == max(a - ov, 0) and gb == min(b + ov + 7, h)
+        else:
+            assert gb == ga
+    assert all(l.band == L.bands[r] for r, l in enumerate(layouts))

@@ -7,7 +7,7 @@ from microaligner_b200 import parallel
 from oracle import reference_flow as rf
 
 
-@settings(max_examples=40, deadline=None)
+@settings(max_examples=40, deadline=None, derandomize=True)
 @given(h=st.integers(100, 900), w=st.integers(100, 900), T=st.integers(20, 400), data=st.data())
 def test_split_stitch_roundtrip(h, w, T, data):
     ov = data.draw(st.integers(10, max(10, min(T, 60))))
@@ -23,7 +23,7 @@ def test_split_stitch_roundtrip(h, w, T, data):
     assert np.array_equal(t0[ov:ov + min(T, h), ov:ov + min(T, w)], a[:min(T, h), :min(T, w)])
 
 
-@settings(max_examples=60, deadline=None)
+@settings(max_examples=60, deadline=None, derandomize=True)
 @given(ny=st.integers(1, 40), nx=st.integers(1, 40), world=st.integers(1, 9), T=st.integers(20, 300), data=st.data())
 def test_tile_and_band_partitions_cover_exactly_once(ny, nx, world, T, data):
     h = (ny - 1) * T + data.draw(st.integers(1, T))
@@ -40,7 +40,7 @@ def test_tile_and_band_partitions_cover_exactly_once(ny, nx, world, T, data):
     assert (cover == 1).all()
 
 
-@settings(max_examples=40, deadline=None)
+@settings(max_examples=40, deadline=None, derandomize=True)
 @given(ny=st.integers(1, 12), nx=st.integers(1, 8), world=st.integers(2, 8), ov=st.integers(0, 40))
 def test_rect_plan_delivers_every_needed_row_once(ny, nx, world, ov):
     T = 50
@@ -60,7 +60,7 @@ def test_rect_plan_delivers_every_needed_row_once(ny, nx, world, ov):
         assert (got[nd[0]:nd[1]] == 1).all()
 
 
-@settings(max_examples=60, deadline=None)
+@settings(max_examples=60, deadline=None, derandomize=True)
 @given(h=st.integers(50, 5000), w=st.integers(50, 5000), T=st.integers(20, 1000), world=st.integers(1, 8))
 def test_nmi_chunks_have_one_owner(h, w, T, world):
     ny = -(-h // T)
@@ -74,7 +74,7 @@ def test_nmi_chunks_have_one_owner(h, w, T, world):
     assert (seen == 1).all()
 
 
-@settings(max_examples=30, deadline=None)
+@settings(max_examples=30, deadline=None, derandomize=True)
 @given(n=st.integers(1, 60), world=st.integers(1, 6), data=st.data())
 def test_row_transfer_plan(n, world, data):
     owned = parallel.split_even(n, world)
