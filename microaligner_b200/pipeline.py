@@ -51,9 +51,15 @@ def optflow_parameters(config: Union[str, Mapping]) -> Dict:
                 use_full_res_img=bool(p.get("UseFullResImage", False)), use_dog=bool(p.get("UseDOG", False)))
 
 
+def _rank0_sink(sink):
+    """With several ranks (parallel.init) every rank runs the same SPMD loop; only rank 0 hands results to the sink."""
+    return sink if parallel.get().rank == 0 else (lambda *a, **k: None)
+
+
 def warp_and_save_pages(sink, cyc, ch, flow: torch.Tensor, pages: Mapping[int, Page], tile_size: int, overlap: int):
     """warp_and_save_pages (__main__.py:288-302) with the flow resident on the device; uploads, warps and
     downloads of consecutive z-planes overlap on two streams."""
+    sink = _rank0_sink(sink)
     eng = Engine(tile_size, overlap, comm=parallel.get())
     streams = [torch.cuda.Stream(), torch.cuda.Stream()]
     cur = torch.cuda.current_stream()
@@ -87,6 +93,7 @@ def register_and_save_ofreg_imgs(dataset: Dataset, ref_channel: Union[str, Mappi
     warper = Warper()
     warper.tile_size, warper.overlap = tile_size, overlap
 
+    sink = _rank0_sink(sink)
     cycles = list(dataset.keys())
     ncycles = len(cycles)
     ref_img: Optional[torch.Tensor] = None
