@@ -51,6 +51,11 @@ def optflow_parameters(config: Union[str, Mapping]) -> Dict:
                 use_full_res_img=bool(p.get("UseFullResImage", False)), use_dog=bool(p.get("UseDOG", False)))
 
 
+def _say(*a):
+    if parallel.get().rank == 0:
+        print(*a)
+
+
 def _rank0_sink(sink):
     """With several ranks (parallel.init) every rank runs the same SPMD loop; only rank 0 hands results to the sink."""
     return sink if parallel.get().rank == 0 else (lambda *a, **k: None)
@@ -99,13 +104,13 @@ def register_and_save_ofreg_imgs(dataset: Dataset, ref_channel: Union[str, Mappi
     ref_img: Optional[torch.Tensor] = None
     decisions = {}
     for cyc_id, cyc in enumerate(cycles):
-        print(f"Processing Cycle {cyc} [{cyc_id + 1}/{ncycles}]")
+        _say(f"Processing Cycle {cyc} [{cyc_id + 1}/{ncycles}]")
         ref_ch = ref_channel[cyc] if isinstance(ref_channel, Mapping) else ref_channel
         zplanes = list(dataset[cyc][ref_ch].values())
         if cyc_id == 0:
-            print("Skipping as it is a reference image")
+            _say("Skipping as it is a reference image")
             ref_img = max_project_pages(zplanes)
-            print(f"Saving Cycle {cyc} [{cyc_id + 1}/{ncycles}]")
+            _say(f"Saving Cycle {cyc} [{cyc_id + 1}/{ncycles}]")
             for ch, pages in dataset[cyc].items():
                 for z, page in pages.items():
                     p = _load(page)
@@ -117,7 +122,7 @@ def register_and_save_ofreg_imgs(dataset: Dataset, ref_channel: Union[str, Mappi
         warper.image, warper.flow = mov_img, flow
         ref_img = warper.warp()                               # reference of the next cycle
         decisions[cyc] = ofreg.decisions
-        print(f"Saving Cycle {cyc} [{cyc_id + 1}/{ncycles}]")
+        _say(f"Saving Cycle {cyc} [{cyc_id + 1}/{ncycles}]")
         for ch, pages in dataset[cyc].items():
             warp_and_save_pages(sink, cyc, ch, flow, pages, tile_size, overlap)
         del flow
@@ -133,7 +138,7 @@ def run_opt_flow_reg(config: Union[str, Mapping], dataset: Dataset, sink, ref_ch
     p = optflow_parameters(config)
     if ref_channel is None:
         ref_channel = config.get("Input", {}).get("ReferenceChannel")
-    print("Performing non-linear optical flow based image registration")
+    _say("Performing non-linear optical flow based image registration")
     register_and_save_ofreg_imgs(dataset, ref_channel, sink, p["tile_size"], p["overlap"], p["num_pyr_lvl"],
                                  p["num_iterations"], p["use_full_res_img"], p["use_dog"])
-    print("Finished\n")
+    _say("Finished\n")
