@@ -7,8 +7,10 @@ the first upload to the returned flow: pyramids, DoG images, flows and the simil
 are device tensors, and per pyramid level only the per-chunk NMI doubles cross to the host.
 
 Inputs may be numpy arrays (result: numpy (H, W, 2) float32, like the reference) or CUDA tensors
-(result: CUDA tensor, for a device-resident hand-off to Warper)."""
-from math import log2
+(result: CUDA tensor, for a device-resident hand-off to Warper).
+
+The loop itself -- pyramids, pre-warp, [DoG], tiled Farneback, post-warp, NMI gate, merge / up-sample, written
+once for 1..N GPUs -- lives in microaligner_b200/engine.py; this class is the reference-shaped front door."""
 from typing import List, Tuple
 
 import numpy as np
@@ -81,49 +83,6 @@ class OptFlowRegistrator:
         self._tile_flow_calc.num_iter = self.num_iterations
         self._tile_flow_calc.win_size = self.overlap - (1 - self.overlap % 2)
 
-    def _warp(self, img: torch.Tensor, flow: torch.Tensor) -> torch.Tensor:
-        return ops.warp_tiles(img, flow, self.tile_size, self.overlap)
-
-    def _generate_img_pyr(self, arr: torch.Tensor) -> Tuple[List[torch.Tensor], List[int]]:
-        if self.num_pyr_lvl < 0:
-            raise ValueError("Number of pyramid levels cannot be less than 0")
-        if self.num_pyr_lvl == 0 and not self.use_full_res_img:
-            raise ValueError("Number of pyramid levels is 0 and use_full_res_img is False. "
-                             "Please change one of the parameters")
-        pyramid, factors = [], []
-        cur = arr
-        for lvl in range(self.num_pyr_lvl):
-            factor = 2 ** (lvl + 1)
-            if arr.shape[0] / factor < 100 or arr.shape[1] / factor < 100:
-                break
-            cur = ops.pyr_down(cur)
-            pyramid.append(cur)
-            factors.append(factor)
-        pyramid.reverse()
-        factors.reverse()
-        if self.use_full_res_img:
-            pyramid.append(arr)
-            factors.append(1)
-        return pyramid, factors
-
-    def _upscale_flow_to_full_res(self, flow: torch.Tensor, pyramid_factor: int) -> torch.Tensor:
-        full = tuple(self._full_shape)
-        if abs(flow.shape[0] - full[0]) <= 1:
-            return flow
-        num_lvls = int(log2(pyramid_factor))
-        upscaled = flow
-        for i in range(num_lvls):
-            # the reference restarts from `flow` every pass and does NOT scale by 2 (quirk Q2)
-            dst = full if i == num_lvls - 1 else (2 * flow.shape[0], 2 * flow.shape[1])
-            upscaled = ops.pyr_up_flow(flow, dst, 1.0)
-        return upscaled
-
-    def _merge_list_of_flows(self, flow_list: List[torch.Tensor]) -> torch.Tensor:
-        m_flow = flow_list[0]
-        for f in flow_list[1:]:
-            m_flow = ops.merge_flows_tiles(m_flow, f, self.tile_size, self.overlap)
-        return m_flow
-
     def get_dog_sigmas(self, pyr_factor: int) -> Tuple[int, int]:
         if pyr_factor > 16:
             return 1, 2
@@ -152,7 +111,6 @@ class OptFlowRegistrator:
 
         ref = ops.to_device(self._ref_img)
         mov = ops.to_device(self._mov_img, ref.device)
-        self._full_shape = tuple(ref.shape)
         eng = Engine(self.tile_size, self.overlap, self.num_pyr_lvl, self.num_iterations, self.use_full_res_img,
                      self.use_dog, comm=parallel.get(), contract_fma=not self.exact_arithmetic,
                      corrected=self.corrected_composition)
