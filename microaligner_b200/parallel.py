@@ -79,7 +79,7 @@ def tile_range_rects(tiles: Range, nx: int, T: int, h: int, w: int) -> List[Rect
     return out
 
 
-def rect_plan(have: Sequence[Sequence[Rect]], owned_rows: Sequence[Range], need_rows: Sequence[Range]):
+def rect_plan(have: Sequence[Sequence[Rect]], need_rows: Sequence[Range]):
     """(src, dst, rect): the part of every rectangle rank `src` holds that rank `dst` needs (full-width row
     range need_rows[dst]) and does not hold itself."""
     plan = []
@@ -166,7 +166,7 @@ class Comm:
         """Rank q holds the rectangles have[q] of `t` (rows x columns); make rows need_rows[rank] valid here."""
         if self.world == 1:
             return t
-        mine = [p for p in rect_plan(have, None, need_rows) if self.rank in (p[0], p[1])]
+        mine = [p for p in rect_plan(have, need_rows) if self.rank in (p[0], p[1])]
         if not mine:
             return t
         tw = self._wire(t)

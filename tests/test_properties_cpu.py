@@ -48,7 +48,7 @@ def test_rect_plan_delivers_every_needed_row_once(ny, nx, world, ov):
     have = [parallel.tile_range_rects(t, nx, T, h, w) for t in parallel.split_even(ny * nx, world)]
     bands = [(a * T, min(b * T, h)) for a, b in parallel.split_even(ny, world)]
     need = [(max(a - ov, 0), min(b + ov, h)) if b > a else (a, a) for a, b in bands]
-    plan = parallel.rect_plan(have, None, need)
+    plan = parallel.rect_plan(have, need)
     for dst, nd in enumerate(need):
         got = np.zeros((h, w), np.int32)
         for (y0, y1, x0, x1) in have[dst]:
