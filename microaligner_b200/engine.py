@@ -2,10 +2,12 @@
 (optflow_reg/optflow_registrator.py:93-173) on device tensors, written once for 1..N GPUs.
 
 Sharding (parallel.Comm): at every tiled pyramid level rank r owns a contiguous band of
-tile rows.  Each stage computes only the image rows it owns; what a later stage needs beyond the band
-(tile-window overlap, the 20-row DoG halo, the rows an NMI chunk runs past the band, the rows pyrUp
-reads) is fetched from the owner with point-to-point row exchanges.  Global scalars -- DoG min/max and
-the per-chunk NMI scores -- are all-reduced, so every rank takes the same Better/Worse decision.
+tile rows, and -- independently, for balance -- an equal share of the level's TILES for the Farneback
+flow, which is 4/5 of the work.  Each stage computes only what it owns; what a later stage needs beyond
+that (tile-window overlap, the 20-row DoG halo, the rows an NMI chunk runs past the band, the rows pyrUp
+reads, the centres of off-band Farneback tiles) is fetched from the owner with point-to-point row /
+rectangle exchanges.  Global scalars -- DoG min/max and the per-chunk NMI scores -- are all-reduced
+(one collective per batch), so every rank takes the same Better/Worse decision.
 Levels the reference computes untiled (max(shape)/tile_size < 2) are tiny and run replicated.
 With one rank every exchange is a no-op and the code below is simply the single-GPU path."""
 import contextlib
