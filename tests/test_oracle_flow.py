@@ -54,8 +54,8 @@ def test_forced_decisions_match_reference(monkeypatch, decisions, full_res):
     mod = ref_shim.load()
     import importlib
     ofr = importlib.import_module("microaligner.optflow_reg.optflow_registrator")
-    ref, mov = synth_pair(520, 640, 3, np.uint16)
-    kw = dict(num_pyr_lvl=2, num_iterations=1, tile_size=150, overlap=20, use_full_res_img=full_res)
+    ref, mov = synth_pair(420, 500, 3, np.uint16)
+    kw = dict(num_pyr_lvl=2, num_iterations=1, tile_size=120, overlap=16, use_full_res_img=full_res)
     dec = list(decisions if full_res else decisions[:2])
     it = iter(dec)
     monkeypatch.setattr(ofr, "check_if_higher_similarity", lambda *a, **k: [next(it)])
