@@ -7,14 +7,15 @@ environment, and at GPU speed the pipeline is I/O bound, so this module provides
 Python + numpy, for the only pixel layout the pipeline produces and that a B200 can be fed at line rate:
 
 * classic TIFF ("II*\\0" / "MM\\0*") and BigTIFF ("II+\\0"), any byte order;
-* single-sample, unsigned 8 / 16 bit (or 32-bit float) pages, Compression = 1 (none), strips only;
-* pages whose strips are contiguous in the file are returned as zero-copy ``np.memmap`` views
+* single-sample, unsigned 8 / 16 bit (or 32-bit float) pages in strips or tiles; uncompressed, deflate or LZW
+  (decoded on the host; horizontal predictor supported) -- the fast path is the uncompressed one;
+* uncompressed pages whose strips are contiguous in the file are returned as zero-copy ``np.memmap`` views
   (``TiffPage.asarray()``), or read straight into a caller-supplied, page-locked array (``read_into``) so the next
   H2D copy is a single DMA transfer;
 * ``memmap(path, shape, dtype, description)`` creates a contiguous multi-page BigTIFF and returns the pixel block
   as one writeable ``np.memmap`` of the requested shape -- the reference's output idiom.
 
-Anything else (compression, tiles, multiple samples, sub-IFDs) raises ``TiffFormatError`` rather than guessing."""
+Anything else (JPEG / other codecs, multiple samples, sub-IFDs) raises ``TiffFormatError`` rather than guessing."""
 import mmap
 import os
 import struct
@@ -26,6 +27,7 @@ import numpy as np
 IMAGE_WIDTH, IMAGE_LENGTH, BITS_PER_SAMPLE, COMPRESSION, PHOTOMETRIC = 256, 257, 258, 259, 262
 IMAGE_DESCRIPTION, STRIP_OFFSETS, SAMPLES_PER_PIXEL, ROWS_PER_STRIP, STRIP_BYTE_COUNTS = 270, 273, 277, 278, 279
 PLANAR_CONFIG, SOFTWARE, SAMPLE_FORMAT, TILE_WIDTH = 284, 305, 339, 322
+PREDICTOR, TILE_LENGTH, TILE_OFFSETS, TILE_BYTE_COUNTS = 317, 323, 324, 325
 
 _TYPE_SIZES = {1: 1, 2: 1, 3: 2, 4: 4, 5: 8, 6: 1, 7: 1, 8: 2, 9: 4, 10: 8, 11: 4, 12: 8, 16: 8, 17: 8, 18: 8}
 _TYPE_FMT = {1: "B", 2: "c", 3: "H", 4: "I", 6: "b", 7: "B", 8: "h", 9: "i", 11: "f", 12: "d", 16: "Q", 17: "q", 18: "Q"}
@@ -33,6 +35,41 @@ _TYPE_FMT = {1: "B", 2: "c", 3: "H", 4: "I", 6: "b", 7: "B", 8: "h", 9: "i", 11:
 
 class TiffFormatError(ValueError):
     pass
+
+
+def _lzw_decode(data: bytes, expected: int) -> bytes:
+    """TIFF LZW (MSB-first codes, 9..12 bits, ClearCode 256, EOI 257, 'early change')."""
+    out = bytearray()
+    table = [bytes([i]) for i in range(256)] + [b"", b""]
+    bits, nbits, pos, n = 0, 0, 0, len(data)
+    width, prev = 9, None
+    while True:
+        while nbits < width and pos < n:
+            bits = (bits << 8) | data[pos]
+            pos += 1
+            nbits += 8
+        if nbits < width:
+            break
+        code = (bits >> (nbits - width)) & ((1 << width) - 1)
+        nbits -= width
+        if code == 257:
+            break
+        if code == 256:
+            table = table[:258]
+            width, prev = 9, None
+            continue
+        if prev is None:
+            entry = table[code]
+        else:
+            entry = table[code] if code < len(table) else prev + prev[:1]
+            table.append(prev + entry[:1])
+        out += entry
+        prev = entry
+        if len(table) >= (1 << width) - 1 and width < 12:
+            width += 1
+        if len(out) >= expected:
+            break
+    return bytes(out[:expected])
 
 
 class TiffPage:
@@ -44,24 +81,44 @@ class TiffPage:
         bits = int(tags.get(BITS_PER_SAMPLE, (1,))[0])
         spp = int(tags.get(SAMPLES_PER_PIXEL, (1,))[0])
         fmt = int(tags.get(SAMPLE_FORMAT, (1,))[0])
-        comp = int(tags.get(COMPRESSION, (1,))[0])
-        if comp != 1:
-            raise TiffFormatError(f"compressed TIFF (Compression={comp}) is not supported")
+        self.compression = int(tags.get(COMPRESSION, (1,))[0])
+        self.predictor = int(tags.get(PREDICTOR, (1,))[0])
+        if self.compression not in (1, 5, 8, 32946):
+            raise TiffFormatError(f"compressed TIFF (Compression={self.compression}) is not supported "
+                                  "(none, LZW and deflate are)")
+        if self.predictor not in (1, 2):
+            raise TiffFormatError(f"Predictor={self.predictor} is not supported")
         if spp != 1:
             raise TiffFormatError(f"SamplesPerPixel={spp}: only single-channel pages are supported")
-        if TILE_WIDTH in tags:
-            raise TiffFormatError("tiled TIFF is not supported (strips only)")
         kinds = {(8, 1): "u1", (16, 1): "u2", (32, 1): "u4", (32, 3): "f4", (16, 2): "i2", (8, 2): "i1"}
         if (bits, fmt) not in kinds:
             raise TiffFormatError(f"unsupported sample type: {bits} bits, SampleFormat {fmt}")
         self.dtype = np.dtype(tif.byteorder + kinds[(bits, fmt)]) if bits > 8 else np.dtype(kinds[(bits, fmt)])
         self.shape = (self.height, self.width)
-        self.offsets = [int(v) for v in tags[STRIP_OFFSETS]]
-        self.counts = [int(v) for v in tags[STRIP_BYTE_COUNTS]]
         self.nbytes = self.height * self.width * self.dtype.itemsize
-        if sum(self.counts) != self.nbytes:
+        # segments: (file offset, byte count, y0, x0, rows, cols) -- strips or tiles
+        self.segments = []
+        if TILE_WIDTH in tags:
+            tw, tl = int(tags[TILE_WIDTH][0]), int(tags[TILE_LENGTH][0])
+            offs, cnts = tags[TILE_OFFSETS], tags[TILE_BYTE_COUNTS]
+            across = -(-self.width // tw)
+            for i, (o, c) in enumerate(zip(offs, cnts)):
+                self.segments.append((int(o), int(c), (i // across) * tl, (i % across) * tw, tl, tw))
+            self.tiled = True
+        else:
+            rps = int(tags.get(ROWS_PER_STRIP, (self.height,))[0])
+            rps = min(rps, self.height) or self.height
+            for i, (o, c) in enumerate(zip(tags[STRIP_OFFSETS], tags[STRIP_BYTE_COUNTS])):
+                y0 = i * rps
+                self.segments.append((int(o), int(c), y0, 0, min(rps, self.height - y0), self.width))
+            self.tiled = False
+        self.offsets = [sg[0] for sg in self.segments]
+        self.counts = [sg[1] for sg in self.segments]
+        plain = self.compression == 1 and not self.tiled
+        if plain and sum(self.counts) != self.nbytes:
             raise TiffFormatError("strip byte counts do not add up to an uncompressed page")
-        self.is_contiguous = all(self.offsets[i] + self.counts[i] == self.offsets[i + 1] for i in range(len(self.offsets) - 1))
+        self.is_contiguous = plain and all(self.offsets[i] + self.counts[i] == self.offsets[i + 1]
+                                           for i in range(len(self.offsets) - 1))
 
     @property
     def description(self) -> Optional[str]:
@@ -69,31 +126,44 @@ class TiffPage:
         return v[0] if v else None
 
     def asarray(self) -> np.ndarray:
-        """The page as a (height, width) array in native byte order; zero-copy memmap view when possible."""
+        """The page as a (height, width) array in native byte order; a zero-copy memmap view for uncompressed pages
+        whose strips are contiguous in the file."""
         if self.is_contiguous:
             a = np.ndarray(self.shape, self.dtype, buffer=self._tif._map, offset=self.offsets[0])
-        else:
-            buf = bytearray(self.nbytes)
-            self._read_strips(memoryview(buf))
-            a = np.frombuffer(buf, self.dtype).reshape(self.shape)
-        if not a.dtype.isnative:
-            a = a.astype(a.dtype.newbyteorder("="))
-        return a
+            return a if a.dtype.isnative else a.astype(a.dtype.newbyteorder("="))
+        return self.read_into(np.empty(self.shape, self.dtype.newbyteorder("=")))
 
     def read_into(self, out: np.ndarray) -> np.ndarray:
         """Fill a caller-owned (e.g. page-locked) array of the page's shape and dtype."""
         if out.shape != self.shape or out.dtype.itemsize != self.dtype.itemsize or not out.flags.c_contiguous:
             raise ValueError(f"read_into needs a C-contiguous array of shape {self.shape} and item size {self.dtype.itemsize}")
-        self._read_strips(memoryview(out.reshape(-1).view(np.uint8)))
-        if not self.dtype.isnative:
-            out.byteswap(inplace=True)
+        if self.compression == 1 and not self.tiled:
+            dst = memoryview(out.reshape(-1).view(np.uint8))
+            pos = 0
+            for off, n in zip(self.offsets, self.counts):
+                dst[pos:pos + n] = self._tif._map[off:off + n]
+                pos += n
+            if not self.dtype.isnative:
+                out.byteswap(inplace=True)
+            return out
+        for off, n, y0, x0, rows, cols in self.segments:
+            raw = self._tif._map[off:off + n]
+            want = rows * cols * self.dtype.itemsize
+            if self.compression in (8, 32946):
+                import zlib
+                raw = zlib.decompress(raw)
+            elif self.compression == 5:
+                raw = _lzw_decode(bytes(raw), want)
+            if len(raw) < want:
+                raise TiffFormatError("truncated TIFF segment")
+            seg = np.frombuffer(raw, self.dtype, count=rows * cols).reshape(rows, cols)
+            if not seg.dtype.isnative:
+                seg = seg.astype(seg.dtype.newbyteorder("="))
+            if self.predictor == 2:          # horizontal differencing, wraps modulo 2^bits
+                seg = np.cumsum(seg, axis=1, dtype=seg.dtype)
+            y1, x1 = min(y0 + rows, self.height), min(x0 + cols, self.width)
+            out[y0:y1, x0:x1] = seg[:y1 - y0, :x1 - x0].view(out.dtype)
         return out
-
-    def _read_strips(self, dst: memoryview):
-        pos = 0
-        for off, n in zip(self.offsets, self.counts):
-            dst[pos:pos + n] = self._tif._map[off:off + n]
-            pos += n
 
 
 class TiffSeries:

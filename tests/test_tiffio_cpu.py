@@ -86,10 +86,80 @@ def test_big_endian_and_multi_strip(tmp_path):
         assert np.array_equal(pg.read_into(out), img.astype(np.uint16))
 
 
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16])
+@pytest.mark.parametrize("comp", ["tiff_lzw", "tiff_adobe_deflate"])
+@pytest.mark.parametrize("predictor", [False, True])
+def test_compressed_strips_written_by_libtiff(tmp_path, dtype, comp, predictor):
+    """LZW / deflate strips, with and without the horizontal predictor, decode to what libtiff encoded."""
+    rng = np.random.default_rng(5)
+    ramp = np.add.outer(np.arange(300), np.arange(410)) * (np.iinfo(dtype).max // 800)
+    a = (ramp + rng.integers(0, 4, ramp.shape)).astype(dtype)          # smooth + noise: long and short LZW strings
+    a[100:140] = rng.integers(0, np.iinfo(dtype).max, (40, 410))       # incompressible band: table resets
+    p = tmp_path / "c.tif"
+    PIL.fromarray(a).save(p, compression=comp, **({"tiffinfo": {317: 2}} if predictor else {}))
+    with tiffio.TiffFile(p) as tif:
+        pg = tif.pages[0]
+        assert pg.compression in (5, 8) and pg.predictor == (2 if predictor else 1) and not pg.is_contiguous
+        assert np.array_equal(pg.asarray(), a)
+        out = np.empty(a.shape, dtype)
+        assert np.array_equal(pg.read_into(out), a)
+
+
+def _tiled_tiff(img, tile, compress):
+    """Hand-built little-endian classic TIFF with TileWidth/TileLength and optional deflate."""
+    import zlib
+    h, w = img.shape
+    tl, tw = tile
+    blobs = []
+    for y in range(0, h, tl):
+        for x in range(0, w, tw):
+            t = np.zeros((tl, tw), img.dtype)
+            part = img[y:y + tl, x:x + tw]
+            t[:part.shape[0], :part.shape[1]] = part
+            raw = t.tobytes()
+            blobs.append(zlib.compress(raw) if compress else raw)
+    n = len(blobs)
+    offs, pos = [], 8
+    for b in blobs:
+        offs.append(pos)
+        pos += len(b) + (len(b) & 1)
+    arr_off = pos
+    ifd_off = arr_off + 8 * n
+    body = bytearray(b"II" + struct.pack("<HI", 42, ifd_off))
+    for b in blobs:
+        body += b + b"\x00" * (len(b) & 1)
+    body += struct.pack(f"<{n}I", *offs) + struct.pack(f"<{n}I", *[len(b) for b in blobs])
+    bits = img.dtype.itemsize * 8
+    entries = [(256, 3, 1, w), (257, 3, 1, h), (258, 3, 1, bits), (259, 3, 1, 8 if compress else 1), (262, 3, 1, 1),
+               (277, 3, 1, 1), (322, 3, 1, tw), (323, 3, 1, tl), (324, 4, n, arr_off), (325, 4, n, arr_off + 4 * n),
+               (339, 3, 1, 1)]
+    body += struct.pack("<H", len(entries))
+    for tag, typ, cnt, val in entries:
+        if typ == 3 and cnt == 1:
+            body += struct.pack("<HHIHH", tag, typ, cnt, val, 0)
+        else:
+            body += struct.pack("<HHII", tag, typ, cnt, val)
+    body += struct.pack("<I", 0)
+    return bytes(body)
+
+
+@pytest.mark.parametrize("compress", [False, True])
+def test_tiled_pages(tmp_path, compress):
+    """Tiled pages (the layout pyramidal OME-TIFF writers use), ragged edge tiles included; cross-checked with libtiff."""
+    a = np.random.default_rng(2).integers(0, 65535, (70, 100)).astype(np.uint16)
+    p = tmp_path / "tiled.tif"
+    p.write_bytes(_tiled_tiff(a, (32, 48), compress))
+    assert np.array_equal(np.array(PIL.open(p)), a)                    # the hand-built file is a valid TIFF
+    with tiffio.TiffFile(p) as tif:
+        pg = tif.pages[0]
+        assert pg.tiled and len(pg.segments) == 9 and not pg.is_contiguous
+        assert np.array_equal(pg.asarray(), a)
+
+
 def test_unsupported_files_fail_loudly(tmp_path):
-    a = pages(1)[0]
-    p = tmp_path / "lzw.tif"
-    PIL.fromarray(a).save(p, compression="tiff_lzw")
+    a = pages(1)[0].astype(np.uint8)
+    p = tmp_path / "jpeg.tif"
+    PIL.fromarray(a).save(p, compression="jpeg")
     with pytest.raises(tiffio.TiffFormatError, match="compressed"):
         tiffio.TiffFile(p)
     rgb = np.zeros((8, 8, 3), np.uint8)
