@@ -67,6 +67,16 @@ int ma_warp_tiles(const void* img, size_t img_pitch, int dtype, const float* flo
 int ma_warp_tiles_rows(const void* img, size_t img_pitch, int dtype, const float* flow, int h, int w,
                        int T, int ov, void* out, size_t out_pitch, int row_begin, int row_end, void* stream);
 
+/* ---- transform_img_with_tmat (shared_modules/utils.py:98-114, exported at microaligner/__init__.py:20):
+ * pad_to_shape (utils.py:53-66) fused with skimage.transform.warp(img, AffineTransform(inv), order=1,
+ * mode='constant', cval=0, preserve_range=True).astype(dtype).  `inv3x3` is a HOST pointer to the 9 doubles
+ * (row-major) of the output(x, y, 1) -> input matrix, i.e. pinv([[tmat], [0, 0, 1]]) as the reference computes
+ * it; float64 arithmetic, metric / affine / projective coordinate transform chosen from the matrix like
+ * skimage's _warp_fast.  The src_h x src_w page sits at (pad_top, pad_left) of the zero out_h x out_w frame.
+ * dtype MA_U8 | MA_U16.  img and out must not overlap. */
+int ma_warp_affine(const void* img, size_t img_pitch, int dtype, int src_h, int src_w, int pad_top, int pad_left,
+                   const double* inv3x3, void* out, size_t out_pitch, int out_h, int out_w, void* stream);
+
 /* ---- merge_two_flows per tile + stitch (optflow_reg/optflow_registrator.py:37-47, 217-240):
  * per tile: max(f1)==0 -> f2; max(f2)==0 -> f1; else f1 + remap(f2, map = -f1).
  * workspace: ma_merge_workspace_bytes(h, w, T). */

@@ -32,6 +32,8 @@ PROTOTYPES = {
     "ma_pyrup_flow": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_float, c_void_p]),
     "ma_warp_tiles": (c_int, [c_void_p, c_size_t, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "ma_warp_tiles_rows": (c_int, [c_void_p, c_size_t, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_int, c_int, c_void_p]),
+    "ma_warp_affine": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_double), c_void_p, c_size_t,
+                               c_int, c_int, c_void_p]),
     "ma_pyrup_flow_rows": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_float, c_int, c_int, c_void_p]),
     "ma_merge_flows_tile_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "ma_dog_diff_pitch_floats": (c_size_t, [c_int]),

@@ -15,7 +15,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 static const char* kKernelNames[K_COUNT] = {
     "fb_polyexp", "fb_update", "fb_blur_v", "fb_blur_h", "warp_tiles", "tile_max", "merge_tiles", "pyrdown", "pyrup_flow",
-    "minmax", "dog_row", "dog_col", "dog_quant", "nmi_hist", "nmi_entropy", "zmip", "norm_u8", "small"};
+    "minmax", "dog_row", "dog_col", "dog_quant", "nmi_hist", "nmi_entropy", "zmip", "norm_u8", "small", "warp_affine"};
 
 static std::atomic<long long> g_launches{0};
 static std::atomic<int> g_prof_on{0};

@@ -28,7 +28,7 @@ int cuda_fail(cudaError_t e, const char* what);
 // ---- launch accounting + optional per-kernel CUDA-event profiler (ma_profile_* in the C ABI) ----
 enum KernelId {
     K_POLYEXP = 0, K_UPDATE0, K_BLUR_V, K_BLUR_H, K_WARP, K_MERGE_MAX, K_MERGE, K_PYRDOWN, K_PYRUP,
-    K_MINMAX, K_DOG_ROW, K_DOG_COL, K_DOG_QUANT, K_NMI_HIST, K_NMI_ENTROPY, K_ZMIP, K_NORM_U8, K_SMALL, K_COUNT
+    K_MINMAX, K_DOG_ROW, K_DOG_COL, K_DOG_QUANT, K_NMI_HIST, K_NMI_ENTROPY, K_ZMIP, K_NORM_U8, K_SMALL, K_AFFINE, K_COUNT
 };
 void prof_begin(int id, cudaStream_t s, double units);
 void prof_end(int id, cudaStream_t s);

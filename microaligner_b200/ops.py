@@ -169,6 +169,24 @@ def warp_tiles_host_streamed(image: np.ndarray, flow: torch.Tensor, tile_size: i
     return out_h.numpy()
 
 
+def warp_affine(img: torch.Tensor, inv3x3: np.ndarray, out_shape: Sequence[int], pad_top: int = 0, pad_left: int = 0) -> torch.Tensor:
+    """The page `img`, placed at (pad_top, pad_left) of a zero frame of out_shape, resampled through the 3x3
+    output->input matrix `inv3x3` with skimage's order-1 / constant-0 / float64 arithmetic (ma_warp_affine)."""
+    _req(img, "image")
+    if img.dim() != 2:
+        raise ValueError("image must be 2-D")
+    m = np.ascontiguousarray(inv3x3, dtype=np.float64)
+    if m.shape != (3, 3):
+        raise ValueError("inv3x3 must be a 3x3 matrix")
+    oh, ow = int(out_shape[0]), int(out_shape[1])
+    out = torch.empty((oh, ow), dtype=img.dtype, device=img.device)
+    es = img.element_size()
+    check(lib.ma_warp_affine(img.data_ptr(), img.stride(0) * es, _code(img), img.shape[0], img.shape[1], int(pad_top), int(pad_left),
+                             m.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), out.data_ptr(), ow * es, oh, ow, _stream()),
+          "ma_warp_affine")
+    return out
+
+
 def merge_flows_tiles(f1: torch.Tensor, f2: torch.Tensor, tile_size: int, overlap: int) -> torch.Tensor:
     _req(f1, "flow1")
     _req(f2, "flow2")

@@ -21,6 +21,7 @@ import torch
 from . import ops, parallel
 from .engine import Engine
 from .optflow_reg import OptFlowRegistrator, Warper
+from .shared_modules.utils import transform_img_with_tmat
 
 Page = Union[np.ndarray, torch.Tensor, Callable[[], np.ndarray]]
 Dataset = Mapping[int, Mapping[str, Mapping[int, Page]]]
@@ -85,6 +86,38 @@ def warp_and_save_pages(sink, cyc, ch, flow: torch.Tensor, pages: Mapping[int, P
     for z0, s0, h0, _, _ in pending:
         s0.synchronize()
         sink(cyc, ch, z0, h0.numpy())
+
+
+def transform_and_save_zplanes(sink, cyc, ch, target_shape, transform_matrix, pages: Mapping[int, Page], max_zplanes: int):
+    """transform_and_save_zplanes (__main__.py:84-112): every z-plane of one channel is padded to target_shape and
+    resampled by the cycle's 2x3 matrix (transform_img_with_tmat); channels with fewer planes than max_zplanes are
+    completed with empty pages.  Uploads, resampling and downloads of consecutive planes overlap on two streams."""
+    sink = _rank0_sink(sink)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    cur = torch.cuda.current_stream()
+    pending, z_id, last = [], 0, None
+    for i, (z, page) in enumerate(pages.items()):
+        s = streams[i % 2]
+        s.wait_stream(cur)
+        with torch.cuda.stream(s):
+            img = ops.to_device(_load(page))
+            out = transform_img_with_tmat(img, target_shape, transform_matrix)
+            host = torch.empty(out.shape, dtype=out.dtype, device="cpu", pin_memory=True)
+            host.copy_(out, non_blocking=True)
+        pending.append((z_id, s, host, img, out))
+        z_id += 1
+        if len(pending) > 1:
+            z0, s0, h0, _, _ = pending.pop(0)
+            s0.synchronize()
+            sink(cyc, ch, z0, h0.numpy())
+            last = h0
+    for z0, s0, h0, _, _ in pending:
+        s0.synchronize()
+        sink(cyc, ch, z0, h0.numpy())
+        last = h0
+    if last is not None:
+        for z0 in range(z_id, max_zplanes):
+            sink(cyc, ch, z0, np.zeros_like(last.numpy()))
 
 
 def register_and_save_ofreg_imgs(dataset: Dataset, ref_channel: Union[str, Mapping[int, str]], sink, tile_size=1000, overlap=100,
