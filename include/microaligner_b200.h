@@ -109,6 +109,16 @@ int ma_farneback_tiles(const void* mov, const void* ref, size_t pitch, int dtype
  * FP32 pipe cycles in the two dominant kernels, results within ~1e-6 px of the default (inside the 0.01 / 0.1 px
  * contract per call) but no longer bit-identical to OpenCV's unfused CPU arithmetic.  Off by default. */
 #define MA_FB_CONTRACT_FMA 1u
+/* MA_FB_PIPELINED: run the window blur as persistent, warp-specialised kernels (TMA producer warp + 8 consumer
+ * warps per CTA, results stored straight from registers).  Same arithmetic, bit-identical results. */
+#define MA_FB_PIPELINED 2u
+/* Experimental window-blur kernel variants, selected per pass (results are bit-identical in all of them):
+ *   flags |= v << MA_FB_VARIANT_SHIFT_V   v: 0 CTA per box + shared-memory transpose (default), 1 persistent TMA ring,
+ *                                            2 CTA per box + stores straight from registers
+ *   flags |= h << MA_FB_VARIANT_SHIFT_H   h: 0 CTA per block + shared-memory flow stage (default), 1 persistent TMA ring,
+ *                                            2 persistent ring with a rolled plane loop, 3 CTA per block + register stores */
+#define MA_FB_VARIANT_SHIFT_V 8
+#define MA_FB_VARIANT_SHIFT_H 12
 int ma_farneback_tiles_ex(const void* mov, const void* ref, size_t pitch, int dtype, int h, int w,
                           int T, int ov, int win, int iters, int tile_begin, int tile_end,
                           float* flow_out, void* workspace, size_t workspace_bytes, unsigned flags, void* stream);

@@ -486,6 +486,415 @@ __global__ void __launch_bounds__(256, 2) fb_blur_h_kernel(const __grid_constant
     }
 }
 
+// ---- epilogues that store straight from the accumulator registers (shared by the experimental variants) ----
+// V pass: V^T[x][y .. y + 7] for the thread's two columns; the row pitch is a multiple of 32 floats, so a full
+// vector never leaves the row even when it runs past Sh (padding, never read back)
+__device__ __forceinline__ void store_vt_strip(const FbBatch& b, int slot, int c, int x, int y, int Sw, const u64 (&acc)[kR]) {
+    float* __restrict__ dst = slot_plane(b, slot, 3, c) + (size_t)x * b.SpT + y;
+    float2 v[kR];
+#pragma unroll
+    for (int j = 0; j < kR; ++j) v[j] = unpack2(acc[j]);
+    if (x < Sw) {
+        reinterpret_cast<float4*>(dst)[0] = make_float4(v[0].x, v[1].x, v[2].x, v[3].x);
+        reinterpret_cast<float4*>(dst)[1] = make_float4(v[4].x, v[5].x, v[6].x, v[7].x);
+    }
+    if (x + 1 < Sw) {
+        reinterpret_cast<float4*>(dst + b.SpT)[0] = make_float4(v[0].y, v[1].y, v[2].y, v[3].y);
+        reinterpret_cast<float4*>(dst + b.SpT)[1] = make_float4(v[4].y, v[5].y, v[6].y, v[7].y);
+    }
+}
+
+__device__ __forceinline__ float2 solve_flow(float g11f, float g12f, float g22f, float h1f, float h2f) {
+    // FarnebackUpdateFlow_GaussianBlur: 2x2 solve in f64
+    const double g11 = g11f, g12 = g12f, g22 = g22f, h1 = h1f, h2 = h2f;
+    const double idet = __ddiv_rn(1.0, __dadd_rn(__dsub_rn(__dmul_rn(g11, g22), __dmul_rn(g12, g12)), 1e-3));
+    float2 o;
+    o.x = (float)__dmul_rn(__dsub_rn(__dmul_rn(g11, h2), __dmul_rn(g12, h1)), idet);
+    o.y = (float)__dmul_rn(__dsub_rn(__dmul_rn(g22, h1), __dmul_rn(g12, h2)), idet);
+    return o;
+}
+
+// H pass: solve and store the thread's 2 rows (y, y + 1) x 8 columns (xb .. xb + 7) -- contiguous along x in the tile
+// flow plane (full 64-byte vectors; the pitch Sp is a multiple of 32) and in the stitched flow (checked per pixel)
+__device__ __forceinline__ void solve_store_strip(const FbBatch& b, int slot, int y0, int xb, int lane, int last_iter,
+                                                  float2* __restrict__ flow_out, const u64 (&a0)[kR], const u64 (&a1)[kR],
+                                                  const u64 (&a2)[kR], const u64 (&a3)[kR], const u64 (&a4)[kR]) {
+    const TileGeom& g = b.g;
+    const int Sh = g.Sh, Sw = g.Sw;
+    const int tile = b.tile0 + slot;
+    const int ti = tile / g.nx, tj = tile - ti * g.nx;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int y = y0 + 2 * lane + half;
+        if (y >= Sh) continue;
+        float2 f[kR];
+#pragma unroll
+        for (int j = 0; j < kR; ++j) {
+            const float2 G11 = unpack2(a0[j]), G12 = unpack2(a1[j]), G22 = unpack2(a2[j]);
+            const float2 H1 = unpack2(a3[j]), H2 = unpack2(a4[j]);
+            f[j] = half ? solve_flow(G11.y, G12.y, G22.y, H1.y, H2.y) : solve_flow(G11.x, G12.x, G22.x, H1.x, H2.x);
+        }
+        if (last_iter) {   // scatter the tile centre into the stitched flow
+            const int cy = y - g.ov, gy = ti * g.Th + cy;
+            if ((unsigned)cy < (unsigned)g.Th && gy < g.h) {
+#pragma unroll
+                for (int j = 0; j < kR; ++j) {
+                    const int cxx = xb + j - g.ov, gx = tj * g.Tw + cxx;
+                    if (xb + j < Sw && (unsigned)cxx < (unsigned)g.Tw && gx < g.w) flow_out[(size_t)gy * g.w + gx] = f[j];
+                }
+            }
+        } else {
+            float4* __restrict__ dst = reinterpret_cast<float4*>(reinterpret_cast<float2*>(slot_plane(b, slot, 4, 0)) + (size_t)y * b.Sp + xb);
+#pragma unroll
+            for (int q = 0; q < kR / 2; ++q) dst[q] = make_float4(f[2 * q].x, f[2 * q].y, f[2 * q + 1].x, f[2 * q + 1].y);
+        }
+    }
+}
+
+// Variant "direct" of fb_blur_v_kernel: same CTA-per-box structure, but no transpose stage and no barrier after the
+// convolution -- every thread writes its outputs with store_vt_strip.
+template <int OUT, bool FUSED>
+__global__ void __launch_bounds__(256) fb_blur_v_direct_kernel(const __grid_constant__ CUtensorMap mapM, FbBatch b,
+                                                               const __grid_constant__ FbConsts cst) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t bar;
+    const int Sh = b.g.Sh, Sw = b.g.Sw, m = cst.m;
+    const int slot = blockIdx.z / 5, c = blockIdx.z % 5;
+    const int x0 = blockIdx.x * kRowF, y0 = blockIdx.y * OUT;
+    const int rows = OUT + 2 * m;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, rows * kRowF * sizeof(float));
+        tma_load_3d(smem, &mapM, x0, y0 - m, slot * kSlotPlanes + 10 + c, &bar);
+    }
+    mbar_wait(&bar, 0);
+    replicate_edges(smem, rows, y0 - m, Sh);
+    const u64 nz = *reinterpret_cast<const u64*>(&cst.negzero2);
+#pragma unroll
+    for (int grp = 0; grp < OUT / 64; ++grp) {
+        const int o0 = grp * 64 + warp * kR;
+        if (y0 + o0 < Sh) {
+            u64 acc[kR];
+            conv8x2<FUSED>(reinterpret_cast<const u64*>(smem) + (o0 + m) * kRowU + lane, m, cst.k2, nz, acc);
+            store_vt_strip(b, slot, c, x0 + 2 * lane, y0 + o0, Sw, acc);
+        }
+    }
+}
+
+// Variant "direct" of fb_blur_h_kernel: same CTA-per-block structure and plane ring, but the flow is solved and
+// stored from registers (no flow stage in shared memory, no barrier after the last plane).
+template <bool FUSED>
+__global__ void __launch_bounds__(256, 2) fb_blur_h_direct_kernel(const __grid_constant__ CUtensorMap mapVT, FbBatch b,
+                                                                   const __grid_constant__ FbConsts cst, int last_iter,
+                                                                   float2* __restrict__ flow_out) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t bars[2];
+    const int Sw = b.g.Sw, m = cst.m;
+    const int slot = blockIdx.z;
+    const int y0 = blockIdx.x * kRowF, x0 = blockIdx.y * kStep;
+    const int rows = kStep + 2 * m;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* buf[2] = {smem, smem + rows * kRowF};
+    const uint32_t box_bytes = rows * kRowF * sizeof(float);
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int c = 0; c < 2; ++c) {
+            mbar_expect_tx(&bars[c], box_bytes);
+            tma_load_3d(buf[c], &mapVT, y0, x0 - m, slot * kSlotPlanes + 15 + c, &bars[c]);
+        }
+    }
+    const u64 nz = *reinterpret_cast<const u64*>(&cst.negzero2);
+    u64 acc[5][kR];
+    const bool active = x0 + warp * kR < Sw;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        mbar_wait(&bars[c & 1], (c >> 1) & 1);
+        replicate_edges(buf[c & 1], rows, x0 - m, Sw);
+        if (active) conv8x2<FUSED>(reinterpret_cast<const u64*>(buf[c & 1]) + (warp * kR + m) * kRowU + lane, m, cst.k2, nz, acc[c]);
+        if (c + 2 < 5) {
+            __syncthreads();  // buffer c&1 is free again
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(&bars[c & 1], box_bytes);
+                tma_load_3d(buf[c & 1], &mapVT, y0, x0 - m, slot * kSlotPlanes + 15 + c + 2, &bars[c & 1]);
+            }
+        }
+    }
+    if (active) solve_store_strip(b, slot, y0, x0 + warp * kR, lane, last_iter, flow_out, acc[0], acc[1], acc[2], acc[3], acc[4]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 (pipelined variant, MA_FB_PIPELINED): the same two passes as persistent kernels without CTA barriers.
+//
+// Grid = 2 CTAs per SM; work items (one 64-output box of one plane for the V pass; one 64 x 64 block of a
+// tile = five boxes for the H pass) are dealt round-robin to the CTAs.  A two-stage ring of TMA boxes with
+// full / empty mbarriers per stage replaces __syncthreads: thread 0 issues the load of box n+1 when it
+// starts box n (the stage it refills was released by all 8 warps after box n-1), every warp convolves its
+// own 8-output strip of the box, releases the stage and writes its results straight from registers -- the 8
+// outputs a thread holds per column are contiguous along the fast axis of the destination (V^T rows for the
+// V pass, flow rows for the H pass), so there is no transpose through shared memory, and the load of the
+// next box, the convolution of this one and the stores of the previous one overlap across warps.
+// Rows outside the tile are not patched in shared memory; edge boxes clamp the row index instead.
+// Arithmetic (order of operations, rounding) is exactly that of conv8x2.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPipeStages = 2;
+constexpr int kPipeWarps = 8;
+constexpr int kPipeThreads = kPipeWarps * 32;
+
+// conv8x2 on a box addressed by row number: col -> this lane's pair in box row 0; output j is centred on box row
+// r0 + j.  EDGE: rows are clamped to [r_lo, r_hi] (the box rows of the first / last row inside the tile).
+template <bool FUSED, bool EDGE>
+__device__ __forceinline__ void conv8x2p(const u64* __restrict__ col, int r0, int r_lo, int r_hi, int m,
+                                         const float2* __restrict__ k2, u64 nz, u64 (&acc)[kR]) {
+    auto row = [&](int r) -> u64 {
+        if (EDGE) r = min(max(r, r_lo), r_hi);
+        return col[r * kRowU];
+    };
+    u64 wp[kR], wm[kR];
+    const u64 k0 = *reinterpret_cast<const u64*>(&k2[0]);
+#pragma unroll
+    for (int j = 0; j < kR; ++j) {
+        u64 c = row(r0 + j);
+        wp[j] = c;
+        wm[j] = c;
+        acc[j] = mul2(c, k0, nz);
+    }
+    int i = 1;
+#pragma unroll 1
+    for (; i + kR - 1 <= m; i += kR) {
+#pragma unroll
+        for (int s = 0; s < kR; ++s) {
+            wp[s] = row(r0 + kR - 1 + i + s);
+            wm[(63 - s) & 7] = row(r0 - i - s);
+            const u64 kk = *reinterpret_cast<const u64*>(&k2[i + s]);
+#pragma unroll
+            for (int j = 0; j < kR; ++j) {
+                const u64 pr = add2(wp[(j + s + 1) & 7], wm[(j + 63 - s) & 7]);
+                acc[j] = FUSED ? fma2(pr, kk, acc[j]) : add2(acc[j], mul2(pr, kk, nz));
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < kR - 1; ++s) {
+        if (i + s <= m) {
+            wp[s] = row(r0 + kR - 1 + i + s);
+            wm[(63 - s) & 7] = row(r0 - i - s);
+            const u64 kk = *reinterpret_cast<const u64*>(&k2[i + s]);
+#pragma unroll
+            for (int j = 0; j < kR; ++j) {
+                const u64 pr = add2(wp[(j + s + 1) & 7], wm[(j + 63 - s) & 7]);
+                acc[j] = FUSED ? fma2(pr, kk, acc[j]) : add2(acc[j], mul2(pr, kk, nz));
+            }
+        }
+    }
+}
+
+// one strip of one box: v_first = coordinate (along the convolution axis) of box row 0, n = tile extent
+template <bool FUSED>
+__device__ __forceinline__ void conv_strip(const float* buf, int lane, int strip, int rows, int v_first, int n, int m,
+                                           const float2* __restrict__ k2, u64 nz, u64 (&acc)[kR]) {
+    const u64* col = reinterpret_cast<const u64*>(buf) + lane;
+    const int r0 = strip * kR + m;
+    if (v_first >= 0 && v_first + rows <= n) conv8x2p<FUSED, false>(col, r0, 0, 0, m, k2, nz, acc);
+    else conv8x2p<FUSED, true>(col, r0, -v_first, n - 1 - v_first, m, k2, nz, acc);
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(kPipeThreads, 2) fb_blur_v_pipe_kernel(const __grid_constant__ CUtensorMap mapM, FbBatch b,
+                                                                         const __grid_constant__ FbConsts cst) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t full[kPipeStages], empty[kPipeStages];
+    const int Sh = b.g.Sh, Sw = b.g.Sw, m = cst.m;
+    const int rows = kStep + 2 * m;
+    const int nbx = (Sw + kRowF - 1) / kRowF, nby = (Sh + kStep - 1) / kStep;
+    const int per_plane = nbx * nby;
+    const int total = per_plane * 5 * b.ntiles;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kPipeStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kPipeWarps);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    // box nn of this CTA = item blockIdx.x + nn * gridDim.x, loaded into stage nn % 2 (its use number nn / 2)
+    auto issue = [&](int nn) {
+        const int item = blockIdx.x + nn * gridDim.x;
+        if (item >= total) return;
+        const int s = nn % kPipeStages, use = nn / kPipeStages;
+        if (use > 0) mbar_wait_guarded(&empty[s], (use - 1) & 1);   // all warps released the box that sat here before
+        const int pl = item / per_plane, rem = item - pl * per_plane;
+        const int by = rem / nbx, bx = rem - by * nbx;
+        const int slot = pl / 5, c = pl - slot * 5;
+        mbar_expect_tx(&full[s], rows * kRowF * sizeof(float));
+        tma_load_3d(smem + (size_t)s * rows * kRowF, &mapM, bx * kRowF, by * kStep - m, slot * kSlotPlanes + 10 + c, &full[s]);
+    };
+    if (threadIdx.x == 0) {
+        issue(0);
+        issue(1);
+    }
+    const u64 nz = *reinterpret_cast<const u64*>(&cst.negzero2);
+    int n = 0;
+    for (int item = blockIdx.x; item < total; item += gridDim.x, ++n) {
+        if (threadIdx.x == 0 && n > 0) issue(n + 1);
+        __syncwarp();
+        const int s = n % kPipeStages;
+        const int pl = item / per_plane, rem = item - pl * per_plane;
+        const int by = rem / nbx, bx = rem - by * nbx;
+        const int slot = pl / 5, c = pl - slot * 5;
+        const int x0 = bx * kRowF, y0 = by * kStep;
+        const bool active = y0 + warp * kR < Sh;
+        u64 acc[kR];
+        mbar_wait_guarded(&full[s], (n / kPipeStages) & 1);
+        if (active) conv_strip<FUSED>(smem + (size_t)s * rows * kRowF, lane, warp, rows, y0 - m, Sh, m, cst.k2, nz, acc);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);   // this warp no longer reads the stage
+        if (active) {
+            store_vt_strip(b, slot, c, x0 + 2 * lane, y0 + warp * kR, Sw, acc);
+        }
+    }
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(kPipeThreads, 2) fb_blur_h_pipe_kernel(const __grid_constant__ CUtensorMap mapVT, FbBatch b,
+                                                                         const __grid_constant__ FbConsts cst, int last_iter,
+                                                                         float2* __restrict__ flow_out) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t full[kPipeStages], empty[kPipeStages];
+    const TileGeom& g = b.g;
+    const int Sh = g.Sh, Sw = g.Sw, m = cst.m;
+    const int rows = kStep + 2 * m;
+    const int nby = (Sh + kRowF - 1) / kRowF, nbx = (Sw + kStep - 1) / kStep;
+    const int per_tile = nby * nbx;
+    const int total = per_tile * b.ntiles;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kPipeStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kPipeWarps);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    // box nn of this CTA = V^T plane nn % 5 of its item nn / 5, loaded into stage nn % 2 (use number nn / 2)
+    auto issue = [&](int nn) {
+        const int item = blockIdx.x + (nn / 5) * gridDim.x, c = nn % 5;
+        if (item >= total) return;
+        const int s = nn % kPipeStages, use = nn / kPipeStages;
+        if (use > 0) mbar_wait_guarded(&empty[s], (use - 1) & 1);
+        const int slot = item / per_tile, rem = item - slot * per_tile;
+        const int bx = rem / nby, by = rem - bx * nby;
+        mbar_expect_tx(&full[s], rows * kRowF * sizeof(float));
+        tma_load_3d(smem + (size_t)s * rows * kRowF, &mapVT, by * kRowF, bx * kStep - m, slot * kSlotPlanes + 15 + c, &full[s]);
+    };
+    if (threadIdx.x == 0) {
+        issue(0);
+        issue(1);
+    }
+    const u64 nz = *reinterpret_cast<const u64*>(&cst.negzero2);
+    int n = 0;
+    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        const int slot = item / per_tile, rem = item - slot * per_tile;
+        const int bx = rem / nby, by = rem - bx * nby;
+        const int y0 = by * kRowF, x0 = bx * kStep;
+        const bool active = x0 + warp * kR < Sw;
+        u64 acc[5][kR];
+#pragma unroll
+        for (int c = 0; c < 5; ++c, ++n) {
+            if (threadIdx.x == 0 && n > 0) issue(n + 1);
+            __syncwarp();
+            const int s = n % kPipeStages;
+            mbar_wait_guarded(&full[s], (n / kPipeStages) & 1);
+            if (active) conv_strip<FUSED>(smem + (size_t)s * rows * kRowF, lane, warp, rows, x0 - m, Sw, m, cst.k2, nz, acc[c]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+        if (active) solve_store_strip(b, slot, y0, x0 + warp * kR, lane, last_iter, flow_out, acc[0], acc[1], acc[2], acc[3], acc[4]);
+    }
+}
+
+// Variant of fb_blur_h_pipe_kernel with the plane loop NOT unrolled: one copy of the convolution code (the unrolled
+// kernel is ~150 KB of SASS, and its warps -- no longer held together by barriers -- run in different parts of it).
+template <bool FUSED>
+__global__ void __launch_bounds__(kPipeThreads, 2) fb_blur_h_pipe_rolled_kernel(const __grid_constant__ CUtensorMap mapVT, FbBatch b,
+                                                                                const __grid_constant__ FbConsts cst, int last_iter,
+                                                                                float2* __restrict__ flow_out) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t full[kPipeStages], empty[kPipeStages];
+    const TileGeom& g = b.g;
+    const int Sh = g.Sh, Sw = g.Sw, m = cst.m;
+    const int rows = kStep + 2 * m;
+    const int nby = (Sh + kRowF - 1) / kRowF, nbx = (Sw + kStep - 1) / kStep;
+    const int per_tile = nby * nbx;
+    const int total = per_tile * b.ntiles;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kPipeStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kPipeWarps);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    auto issue = [&](int nn) {
+        const int item = blockIdx.x + (nn / 5) * gridDim.x, c = nn % 5;
+        if (item >= total) return;
+        const int s = nn % kPipeStages, use = nn / kPipeStages;
+        if (use > 0) mbar_wait_guarded(&empty[s], (use - 1) & 1);
+        const int slot = item / per_tile, rem = item - slot * per_tile;
+        const int bx = rem / nby, by = rem - bx * nby;
+        mbar_expect_tx(&full[s], rows * kRowF * sizeof(float));
+        tma_load_3d(smem + (size_t)s * rows * kRowF, &mapVT, by * kRowF, bx * kStep - m, slot * kSlotPlanes + 15 + c, &full[s]);
+    };
+    if (threadIdx.x == 0) {
+        issue(0);
+        issue(1);
+    }
+    const u64 nz = *reinterpret_cast<const u64*>(&cst.negzero2);
+    int n = 0;
+    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        const int slot = item / per_tile, rem = item - slot * per_tile;
+        const int bx = rem / nby, by = rem - bx * nby;
+        const int y0 = by * kRowF, x0 = bx * kStep;
+        const bool active = x0 + warp * kR < Sw;
+        u64 a0[kR], a1[kR], a2[kR], a3[kR], cur[kR];
+#pragma unroll 1
+        for (int c = 0; c < 5; ++c, ++n) {
+            if (threadIdx.x == 0 && n > 0) issue(n + 1);
+            __syncwarp();
+            const int s = n % kPipeStages;
+            mbar_wait_guarded(&full[s], (n / kPipeStages) & 1);
+            if (active) conv_strip<FUSED>(smem + (size_t)s * rows * kRowF, lane, warp, rows, x0 - m, Sw, m, cst.k2, nz, cur);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            if (c == 0) {
+#pragma unroll
+                for (int j = 0; j < kR; ++j) a0[j] = cur[j];
+            } else if (c == 1) {
+#pragma unroll
+                for (int j = 0; j < kR; ++j) a1[j] = cur[j];
+            } else if (c == 2) {
+#pragma unroll
+                for (int j = 0; j < kR; ++j) a2[j] = cur[j];
+            } else if (c == 3) {
+#pragma unroll
+                for (int j = 0; j < kR; ++j) a3[j] = cur[j];
+            }
+        }
+        if (active) solve_store_strip(b, slot, y0, x0 + warp * kR, lane, last_iter, flow_out, a0, a1, a2, a3, cur);
+    }
+}
+
 // K2 (iterations > 0): M = UpdateMatrices(R0, R1, flow), one thread per tile pixel, everything coalesced
 // except the bilinear gather of R1 around (x + dx, y + dy).
 __global__ void __launch_bounds__(256) fb_update_kernel(FbBatch b) {
@@ -603,6 +1012,14 @@ extern "C" int ma_farneback_tiles_ex(const void* mov, const void* ref, size_t pi
                                      int T, int ov, int win, int iters, int tile_begin, int tile_end,
                                      float* flow_out, void* workspace, size_t workspace_bytes, unsigned flags, void* stream) {
     const bool fused = (flags & MA_FB_CONTRACT_FMA) != 0;
+    // experimental kernel variants of the window blur (all bit-identical): bits 8..11 V pass, bits 12..15 H pass
+    //   V: 0 CTA per box + smem transpose (default), 1 persistent ring (MA_FB_PIPELINED), 2 CTA per box + register stores
+    //   H: 0 CTA per block + smem flow stage (default), 1 persistent ring, 2 persistent ring with rolled plane loop,
+    //      3 CTA per block + register stores
+    int v_var = (flags >> 8) & 15, h_var = (flags >> 12) & 15;
+    if (flags & MA_FB_PIPELINED) { if (!v_var) v_var = 1; if (!h_var) h_var = 1; }
+    if (v_var > 2 || h_var > 3) return invalid("ma_farneback_tiles: unknown kernel variant");
+    const bool pipelined = v_var == 1;   // the V pass of variant 1 works on 64-output boxes
     if (!mov || !ref || !flow_out || !workspace || h <= 0 || w <= 0) return invalid("ma_farneback_tiles: bad argument");
     if (dtype != MA_U8 && dtype != MA_U16) return invalid("ma_farneback_tiles: dtype must be MA_U8 or MA_U16");
     if (iters < 1) return invalid("ma_farneback_tiles: iterations must be >= 1");
@@ -626,7 +1043,8 @@ extern "C" int ma_farneback_tiles_ex(const void* mov, const void* ref, size_t pi
     make_consts(win, cst);
     cudaStream_t s = (cudaStream_t)stream;
     const int m = cst.m;
-    const int vout = (m <= 49) ? 128 : 64;  // V-pass rows per CTA: box rows vout + 2m must stay <= 256
+    const int vout = (m <= 49 && !pipelined) ? 128 : 64;  // V-pass rows per box: box rows vout + 2m must stay <= 256
+    const size_t pipe_smem = (size_t)kPipeStages * (kStep + 2 * m) * kRowF * sizeof(float);
     const size_t v_smem = std::max((size_t)(vout + 2 * m) * kRowF * sizeof(float), (size_t)kRowF * (vout + 1) * sizeof(float));
     const size_t h_smem = std::max((size_t)2 * (kStep + 2 * m) * kRowF * sizeof(float), (size_t)kStep * kFlowPitch * sizeof(float2));
     static bool attr_set[64] = {false};  // per device
@@ -639,8 +1057,22 @@ extern "C" int ma_farneback_tiles_ex(const void* mov, const void* ref, size_t pi
         MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 256));
         MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 256));
         MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_h_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 256));
+        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeStages * 256 * 256));
+        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeStages * 256 * 256));
+        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_h_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeStages * 256 * 256));
+        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_h_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeStages * 256 * 256));
+        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_h_pipe_rolled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeStages * 256 * 256));
+        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_h_pipe_rolled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeStages * 256 * 256));
+        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_direct_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 256));
+        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_direct_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 256));
+        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_direct_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 256));
+        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_direct_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 256));
+        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_h_direct_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 256));
+        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_h_direct_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 256));
         if (dev_id >= 0 && dev_id < 64) attr_set[dev_id] = true;
     }
+    int n_sm = 148;
+    if (v_var == 1 || h_var == 1 || h_var == 2) MA_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev_id));
     for (int t0 = tile_begin; t0 < tile_end; t0 += cap) {
         FbBatch b;
         b.g = g; b.tile0 = t0; b.ntiles = std::min(cap, tile_end - t0);
@@ -661,16 +1093,42 @@ extern "C" int ma_farneback_tiles_ex(const void* mov, const void* ref, size_t pi
             return MA_ERR_CUDA;
         }
         for (int it = 0; it < iters; ++it) {
+            const bool last = it == iters - 1;
             { KernelScope ks(K_BLUR_V, s, tpx);
-            dim3 vg(ceil_div(g.Sw, kRowF), ceil_div(g.Sh, vout), b.ntiles * 5);
-            if (vout == 128 && !fused) fb_blur_v_kernel<128, false><<<vg, 256, v_smem, s>>>(mapM, b, cst);
-            else if (vout == 128) fb_blur_v_kernel<128, true><<<vg, 256, v_smem, s>>>(mapM, b, cst);
-            else if (!fused) fb_blur_v_kernel<64, false><<<vg, 256, v_smem, s>>>(mapM, b, cst);
-            else fb_blur_v_kernel<64, true><<<vg, 256, v_smem, s>>>(mapM, b, cst); }
+            if (v_var == 1) {
+                const int v_items = ceil_div(g.Sw, kRowF) * ceil_div(g.Sh, kStep) * 5 * b.ntiles;
+                const int vg = std::min(v_items, 2 * n_sm);
+                if (!fused) fb_blur_v_pipe_kernel<false><<<vg, kPipeThreads, pipe_smem, s>>>(mapM, b, cst);
+                else fb_blur_v_pipe_kernel<true><<<vg, kPipeThreads, pipe_smem, s>>>(mapM, b, cst);
+            } else {
+                dim3 vg(ceil_div(g.Sw, kRowF), ceil_div(g.Sh, vout), b.ntiles * 5);
+                if (v_var == 2) {
+                    if (vout == 128 && !fused) fb_blur_v_direct_kernel<128, false><<<vg, 256, v_smem, s>>>(mapM, b, cst);
+                    else if (vout == 128) fb_blur_v_direct_kernel<128, true><<<vg, 256, v_smem, s>>>(mapM, b, cst);
+                    else if (!fused) fb_blur_v_direct_kernel<64, false><<<vg, 256, v_smem, s>>>(mapM, b, cst);
+                    else fb_blur_v_direct_kernel<64, true><<<vg, 256, v_smem, s>>>(mapM, b, cst);
+                } else {
+                    if (vout == 128 && !fused) fb_blur_v_kernel<128, false><<<vg, 256, v_smem, s>>>(mapM, b, cst);
+                    else if (vout == 128) fb_blur_v_kernel<128, true><<<vg, 256, v_smem, s>>>(mapM, b, cst);
+                    else if (!fused) fb_blur_v_kernel<64, false><<<vg, 256, v_smem, s>>>(mapM, b, cst);
+                    else fb_blur_v_kernel<64, true><<<vg, 256, v_smem, s>>>(mapM, b, cst);
+                }
+            } }
             { KernelScope ks(K_BLUR_H, s, tpx);
-            dim3 hg(ceil_div(g.Sh, kRowF), ceil_div(g.Sw, kStep), b.ntiles);
-            if (!fused) fb_blur_h_kernel<false><<<hg, 256, h_smem, s>>>(mapVT, b, cst, it == iters - 1, (float2*)flow_out);
-            else fb_blur_h_kernel<true><<<hg, 256, h_smem, s>>>(mapVT, b, cst, it == iters - 1, (float2*)flow_out); }
+            if (h_var == 1 || h_var == 2) {
+                const int h_items = ceil_div(g.Sh, kRowF) * ceil_div(g.Sw, kStep) * b.ntiles;
+                const int hg = std::min(h_items, 2 * n_sm);
+                if (h_var == 1 && !fused) fb_blur_h_pipe_kernel<false><<<hg, kPipeThreads, pipe_smem, s>>>(mapVT, b, cst, last, (float2*)flow_out);
+                else if (h_var == 1) fb_blur_h_pipe_kernel<true><<<hg, kPipeThreads, pipe_smem, s>>>(mapVT, b, cst, last, (float2*)flow_out);
+                else if (!fused) fb_blur_h_pipe_rolled_kernel<false><<<hg, kPipeThreads, pipe_smem, s>>>(mapVT, b, cst, last, (float2*)flow_out);
+                else fb_blur_h_pipe_rolled_kernel<true><<<hg, kPipeThreads, pipe_smem, s>>>(mapVT, b, cst, last, (float2*)flow_out);
+            } else {
+                dim3 hg(ceil_div(g.Sh, kRowF), ceil_div(g.Sw, kStep), b.ntiles);
+                if (h_var == 3 && !fused) fb_blur_h_direct_kernel<false><<<hg, 256, h_smem, s>>>(mapVT, b, cst, last, (float2*)flow_out);
+                else if (h_var == 3) fb_blur_h_direct_kernel<true><<<hg, 256, h_smem, s>>>(mapVT, b, cst, last, (float2*)flow_out);
+                else if (!fused) fb_blur_h_kernel<false><<<hg, 256, h_smem, s>>>(mapVT, b, cst, last, (float2*)flow_out);
+                else fb_blur_h_kernel<true><<<hg, 256, h_smem, s>>>(mapVT, b, cst, last, (float2*)flow_out);
+            } }
             if (it < iters - 1) {
                 KernelScope ks(K_UPDATE0, s, tpx);
                 fb_update_kernel<<<dim3(ceil_div(g.Sw, 64), ceil_div(g.Sh, 4), b.ntiles), 256, 0, s>>>(b);

@@ -4,6 +4,7 @@ torch is used for device memory, streams and (in parallel.py) the process group 
 arithmetic happens in libmicroaligner_b200.so.  Images are 2-D uint8/uint16 tensors (uint16 is
 carried as torch.uint16), flows are (H, W, 2) float32 tensors, all C-contiguous on one device."""
 import ctypes
+import os
 import weakref
 from typing import Optional, Sequence
 
@@ -201,6 +202,10 @@ def merge_flows_tiles(f1: torch.Tensor, f2: torch.Tensor, tile_size: int, overla
 # --------------------------------------------------------------------------------- Farneback
 _FB_WS = {}
 FARNEBACK_WORKSPACE_BUDGET = 24 << 30  # bytes of HBM the tile batch may use
+# window blur as persistent, barrier-free kernels (MA_FB_PIPELINED): same results; experimental, off by default
+FB_PIPELINED = os.environ.get("MA_FB_PIPELINE", "0") not in ("", "0")
+# experimental window-blur kernel variants "v,h" (MA_FB_VARIANT_SHIFT_V / _H in the header); all bit-identical
+FB_VARIANT = tuple(int(x) for x in os.environ.get("MA_FB_VARIANT", "0,0").split(","))
 
 
 def _fb_workspace(device, nbytes: int) -> torch.Tensor:
@@ -221,9 +226,12 @@ def n_tiles(h: int, w: int, tile_size: int) -> int:
 
 
 def farneback_tiles(mov: torch.Tensor, ref: torch.Tensor, tile_size: int, overlap: int, win: int, iters: int,
-                    tile_range=None, out: Optional[torch.Tensor] = None, contract_fma: bool = False) -> torch.Tensor:
+                    tile_range=None, out: Optional[torch.Tensor] = None, contract_fma: bool = False,
+                    pipelined: Optional[bool] = None, variant: Optional[Sequence[int]] = None) -> torch.Tensor:
     """Stitched flow of the tiled (tile_size > 0) or untiled (tile_size <= 0) Farneback.
-    contract_fma=True trades bit parity for speed in the window blur (MA_FB_CONTRACT_FMA)."""
+    contract_fma=True trades bit parity for speed in the window blur (MA_FB_CONTRACT_FMA).
+    pipelined selects the persistent window-blur kernels (MA_FB_PIPELINED, same results); None = FB_PIPELINED.
+    variant = (v, h) picks experimental window-blur kernels per pass (include/microaligner_b200.h); None = FB_VARIANT."""
     _req(mov, "moving image")
     _req(ref, "reference image")
     if mov.shape != ref.shape or mov.dtype != ref.dtype:
@@ -241,7 +249,9 @@ def farneback_tiles(mov: torch.Tensor, ref: torch.Tensor, tile_size: int, overla
     es = ref.element_size()
     check(lib.ma_farneback_tiles_ex(mov.data_ptr(), ref.data_ptr(), w * es, _code(ref), h, w, T, int(overlap), int(win),
                                     int(iters), int(t0), int(t1), out.data_ptr(), ws.data_ptr(), ws.numel(),
-                                    1 if contract_fma else 0, _stream()), "ma_farneback_tiles")
+                                    (1 if contract_fma else 0) | (2 if (FB_PIPELINED if pipelined is None else pipelined) else 0)
+                                    | (int((variant or FB_VARIANT)[0]) << 8) | (int((variant or FB_VARIANT)[1]) << 12),
+                                    _stream()), "ma_farneback_tiles")
     return out
 
 
