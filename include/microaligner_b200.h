@@ -114,9 +114,10 @@ int ma_farneback_tiles(const void* mov, const void* ref, size_t pitch, int dtype
 #define MA_FB_PIPELINED 2u
 /* Experimental window-blur kernel variants, selected per pass (results are bit-identical in all of them):
  *   flags |= v << MA_FB_VARIANT_SHIFT_V   v: 0 CTA per box + shared-memory transpose (default), 1 persistent TMA ring,
- *                                            2 CTA per box + stores straight from registers
+ *                                            2 CTA per box + stores straight from registers, 3 = 2 with 64-row boxes
  *   flags |= h << MA_FB_VARIANT_SHIFT_H   h: 0 CTA per block + shared-memory flow stage (default), 1 persistent TMA ring,
- *                                            2 persistent ring with a rolled plane loop, 3 CTA per block + register stores */
+ *                                            2 persistent ring with a rolled plane loop, 3 CTA per block + register stores,
+ *                                            4 four outputs per thread (three CTAs per SM) */
 #define MA_FB_VARIANT_SHIFT_V 8
 #define MA_FB_VARIANT_SHIFT_H 12
 int ma_farneback_tiles_ex(const void* mov, const void* ref, size_t pitch, int dtype, int h, int w,

@@ -895,6 +895,135 @@ __global__ void __launch_bounds__(kPipeThreads, 2) fb_blur_h_pipe_rolled_kernel(
     }
 }
 
+// ---- experimental H-pass variant 4: four outputs per thread instead of eight ----
+// The 8-output kernel needs 128 registers (five 8-deep packed accumulators + two windows), which caps the H pass at
+// two CTAs = 16 warps per SM.  With K = 4 the accumulators and windows take 56 registers, three CTAs of 64 y x 32 x
+// fit (boxes of 32 + 2m rows), at the price of twice the shared-memory reads per FP instruction and 1.6x the fill.
+template <int K, bool FUSED>
+__device__ __forceinline__ void convKx2(const u64* __restrict__ centre, int m, const float2* __restrict__ k2, u64 nz, u64 (&acc)[K]) {
+    static_assert(K == 4 || K == 8, "window rotation uses & (K - 1)");
+    u64 wp[K], wm[K];
+    const u64 k0 = *reinterpret_cast<const u64*>(&k2[0]);
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        u64 c = centre[j * kRowU];
+        wp[j] = c;
+        wm[j] = c;
+        acc[j] = mul2(c, k0, nz);
+    }
+    const u64* pp = centre + K * kRowU;   // row of in[K - 1 + i] for i = 1
+    const u64* pm = centre - kRowU;       // row of in[-i] for i = 1
+    int i = 1;
+    // before step i = K g + 1 + s: in[j + i - 1] lives in wp[(j + i - 1) & (K-1)], in[j - i + 1] in wm[(j - i + 1) & (K-1)]
+#pragma unroll 1
+    for (; i + K - 1 <= m; i += K) {
+#pragma unroll
+        for (int s = 0; s < K; ++s) {
+            wp[s] = pp[s * kRowU];
+            wm[(K - 1 - s) & (K - 1)] = pm[-s * kRowU];
+            const u64 kk = *reinterpret_cast<const u64*>(&k2[i + s]);
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const u64 pr = add2(wp[(j + s + 1) & (K - 1)], wm[(j + 8 * K - 1 - s) & (K - 1)]);
+                acc[j] = FUSED ? fma2(pr, kk, acc[j]) : add2(acc[j], mul2(pr, kk, nz));
+            }
+        }
+        pp += K * kRowU;
+        pm -= K * kRowU;
+    }
+#pragma unroll
+    for (int s = 0; s < K - 1; ++s) {
+        if (i + s <= m) {  // warp-uniform tail (m mod K steps)
+            wp[s] = pp[s * kRowU];
+            wm[(K - 1 - s) & (K - 1)] = pm[-s * kRowU];
+            const u64 kk = *reinterpret_cast<const u64*>(&k2[i + s]);
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const u64 pr = add2(wp[(j + s + 1) & (K - 1)], wm[(j + 8 * K - 1 - s) & (K - 1)]);
+                acc[j] = FUSED ? fma2(pr, kk, acc[j]) : add2(acc[j], mul2(pr, kk, nz));
+            }
+        }
+    }
+}
+
+constexpr int kStep4 = 32;   // x outputs per CTA of the 4-output H kernel (8 warps x 4)
+
+template <bool FUSED>
+__global__ void __launch_bounds__(256, 3) fb_blur_h4_kernel(const __grid_constant__ CUtensorMap mapVT, FbBatch b,
+                                                             const __grid_constant__ FbConsts cst, int last_iter,
+                                                             float2* __restrict__ flow_out) {
+    constexpr int K = 4;
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t bars[2];
+    const TileGeom& g = b.g;
+    const int Sh = g.Sh, Sw = g.Sw, m = cst.m;
+    const int slot = blockIdx.z;
+    const int y0 = blockIdx.x * kRowF, x0 = blockIdx.y * kStep4;
+    const int rows = kStep4 + 2 * m;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* buf[2] = {smem, smem + rows * kRowF};
+    const uint32_t box_bytes = rows * kRowF * sizeof(float);
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int c = 0; c < 2; ++c) {
+            mbar_expect_tx(&bars[c], box_bytes);
+            tma_load_3d(buf[c], &mapVT, y0, x0 - m, slot * kSlotPlanes + 15 + c, &bars[c]);
+        }
+    }
+    const u64 nz = *reinterpret_cast<const u64*>(&cst.negzero2);
+    u64 acc[5][K];
+    const int xb = x0 + warp * K;
+    const bool active = xb < Sw;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        mbar_wait(&bars[c & 1], (c >> 1) & 1);
+        replicate_edges(buf[c & 1], rows, x0 - m, Sw);
+        if (active) convKx2<K, FUSED>(reinterpret_cast<const u64*>(buf[c & 1]) + (warp * K + m) * kRowU + lane, m, cst.k2, nz, acc[c]);
+        if (c + 2 < 5) {
+            __syncthreads();  // buffer c&1 is free again
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(&bars[c & 1], box_bytes);
+                tma_load_3d(buf[c & 1], &mapVT, y0, x0 - m, slot * kSlotPlanes + 15 + c + 2, &bars[c & 1]);
+            }
+        }
+    }
+    if (!active) return;
+    // solve + store from registers: rows y0 + 2 lane (+1), columns xb .. xb + 3 (32 contiguous bytes per row)
+    const int tile = b.tile0 + slot;
+    const int ti = tile / g.nx, tj = tile - ti * g.nx;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int y = y0 + 2 * lane + half;
+        if (y >= Sh) continue;
+        float2 f[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const float2 G11 = unpack2(acc[0][j]), G12 = unpack2(acc[1][j]), G22 = unpack2(acc[2][j]);
+            const float2 H1 = unpack2(acc[3][j]), H2 = unpack2(acc[4][j]);
+            f[j] = half ? solve_flow(G11.y, G12.y, G22.y, H1.y, H2.y) : solve_flow(G11.x, G12.x, G22.x, H1.x, H2.x);
+        }
+        if (last_iter) {
+            const int cy = y - g.ov, gy = ti * g.Th + cy;
+            if ((unsigned)cy < (unsigned)g.Th && gy < g.h) {
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    const int cxx = xb + j - g.ov, gx = tj * g.Tw + cxx;
+                    if (xb + j < Sw && (unsigned)cxx < (unsigned)g.Tw && gx < g.w) flow_out[(size_t)gy * g.w + gx] = f[j];
+                }
+            }
+        } else {   // pitch Sp is a multiple of 32: the 32-byte vector stays inside the row
+            float4* __restrict__ dst = reinterpret_cast<float4*>(reinterpret_cast<float2*>(slot_plane(b, slot, 4, 0)) + (size_t)y * b.Sp + xb);
+            dst[0] = make_float4(f[0].x, f[0].y, f[1].x, f[1].y);
+            dst[1] = make_float4(f[2].x, f[2].y, f[3].x, f[3].y);
+        }
+    }
+}
+
 // K2 (iterations > 0): M = UpdateMatrices(R0, R1, flow), one thread per tile pixel, everything coalesced
 // except the bilinear gather of R1 around (x + dx, y + dy).
 __global__ void __launch_bounds__(256) fb_update_kernel(FbBatch b) {
@@ -1013,13 +1142,14 @@ extern "C" int ma_farneback_tiles_ex(const void* mov, const void* ref, size_t pi
                                      float* flow_out, void* workspace, size_t workspace_bytes, unsigned flags, void* stream) {
     const bool fused = (flags & MA_FB_CONTRACT_FMA) != 0;
     // experimental kernel variants of the window blur (all bit-identical): bits 8..11 V pass, bits 12..15 H pass
-    //   V: 0 CTA per box + smem transpose (default), 1 persistent ring (MA_FB_PIPELINED), 2 CTA per box + register stores
+    //   V: 0 CTA per box + smem transpose (default), 1 persistent ring (MA_FB_PIPELINED), 2 CTA per box + register stores,
+    //      3 = 2 with 64-row boxes (more CTAs per SM)
     //   H: 0 CTA per block + smem flow stage (default), 1 persistent ring, 2 persistent ring with rolled plane loop,
-    //      3 CTA per block + register stores
+    //      3 CTA per block + register stores, 4 four outputs per thread (3 CTAs per SM)
     int v_var = (flags >> 8) & 15, h_var = (flags >> 12) & 15;
     if (flags & MA_FB_PIPELINED) { if (!v_var) v_var = 1; if (!h_var) h_var = 1; }
-    if (v_var > 2 || h_var > 3) return invalid("ma_farneback_tiles: unknown kernel variant");
-    const bool pipelined = v_var == 1;   // the V pass of variant 1 works on 64-output boxes
+    if (v_var > 3 || h_var > 4) return invalid("ma_farneback_tiles: unknown kernel variant");
+    const bool pipelined = v_var == 1 || v_var == 3;   // V variants 1 and 3 work on 64-output boxes
     if (!mov || !ref || !flow_out || !workspace || h <= 0 || w <= 0) return invalid("ma_farneback_tiles: bad argument");
     if (dtype != MA_U8 && dtype != MA_U16) return invalid("ma_farneback_tiles: dtype must be MA_U8 or MA_U16");
     if (iters < 1) return invalid("ma_farneback_tiles: iterations must be >= 1");
@@ -1069,6 +1199,8 @@ extern "C" int ma_farneback_tiles_ex(const void* mov, const void* ref, size_t pi
         MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_direct_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 256));
         MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_h_direct_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 256));
         MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_h_direct_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 256));
+        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_h4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 224 * 256));
+        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_h4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 224 * 256));
         if (dev_id >= 0 && dev_id < 64) attr_set[dev_id] = true;
     }
     int n_sm = 148;
@@ -1085,10 +1217,14 @@ extern "C" int ma_farneback_tiles_ex(const void* mov, const void* ref, size_t pi
         else
             fb_polyexp_kernel<uint16_t><<<pg, 256, 0, s>>>((const uint16_t*)mov, (const uint16_t*)ref, pitch, b, cst); }
         // TMA descriptors over this batch's planes: M as [plane][y][x], V^T as [plane][x][y]
-        CUtensorMap mapM, mapVT;
+        CUtensorMap mapM, mapVT, mapVT4;
         uint64_t nplanes = (uint64_t)b.ntiles * kSlotPlanes;
         if (!make_plane_map(&mapM, b.ws, g.Sw, g.Sh, nplanes, (uint64_t)Sp * 4, plane * 4, kRowF, vout + 2 * m) ||
             !make_plane_map(&mapVT, b.ws, g.Sh, g.Sw, nplanes, (uint64_t)SpT * 4, plane * 4, kRowF, kStep + 2 * m)) {
+            set_error("ma_farneback_tiles: cuTensorMapEncodeTiled failed");
+            return MA_ERR_CUDA;
+        }
+        if (h_var == 4 && !make_plane_map(&mapVT4, b.ws, g.Sh, g.Sw, nplanes, (uint64_t)SpT * 4, plane * 4, kRowF, kStep4 + 2 * m)) {
             set_error("ma_farneback_tiles: cuTensorMapEncodeTiled failed");
             return MA_ERR_CUDA;
         }
@@ -1102,7 +1238,7 @@ extern "C" int ma_farneback_tiles_ex(const void* mov, const void* ref, size_t pi
                 else fb_blur_v_pipe_kernel<true><<<vg, kPipeThreads, pipe_smem, s>>>(mapM, b, cst);
             } else {
                 dim3 vg(ceil_div(g.Sw, kRowF), ceil_div(g.Sh, vout), b.ntiles * 5);
-                if (v_var == 2) {
+                if (v_var == 2 || v_var == 3) {
                     if (vout == 128 && !fused) fb_blur_v_direct_kernel<128, false><<<vg, 256, v_smem, s>>>(mapM, b, cst);
                     else if (vout == 128) fb_blur_v_direct_kernel<128, true><<<vg, 256, v_smem, s>>>(mapM, b, cst);
                     else if (!fused) fb_blur_v_direct_kernel<64, false><<<vg, 256, v_smem, s>>>(mapM, b, cst);
@@ -1122,6 +1258,11 @@ extern "C" int ma_farneback_tiles_ex(const void* mov, const void* ref, size_t pi
                 else if (h_var == 1) fb_blur_h_pipe_kernel<true><<<hg, kPipeThreads, pipe_smem, s>>>(mapVT, b, cst, last, (float2*)flow_out);
                 else if (!fused) fb_blur_h_pipe_rolled_kernel<false><<<hg, kPipeThreads, pipe_smem, s>>>(mapVT, b, cst, last, (float2*)flow_out);
                 else fb_blur_h_pipe_rolled_kernel<true><<<hg, kPipeThreads, pipe_smem, s>>>(mapVT, b, cst, last, (float2*)flow_out);
+            } else if (h_var == 4) {
+                dim3 hg(ceil_div(g.Sh, kRowF), ceil_div(g.Sw, kStep4), b.ntiles);
+                const size_t smem4 = (size_t)2 * (kStep4 + 2 * m) * kRowF * sizeof(float);
+                if (!fused) fb_blur_h4_kernel<false><<<hg, 256, smem4, s>>>(mapVT4, b, cst, last, (float2*)flow_out);
+                else fb_blur_h4_kernel<true><<<hg, 256, smem4, s>>>(mapVT4, b, cst, last, (float2*)flow_out);
             } else {
                 dim3 hg(ceil_div(g.Sh, kRowF), ceil_div(g.Sw, kStep), b.ntiles);
                 if (h_var == 3 && !fused) fb_blur_h_direct_kernel<false><<<hg, 256, h_smem, s>>>(mapVT, b, cst, last, (float2*)flow_out);

@@ -1,7 +1,7 @@
 """A/B of the window-blur kernel variants (include/microaligner_b200.h, MA_FB_VARIANT_SHIFT_V / _H): bit-identity of
 the stitched flow against the default kernels over ragged / small-window / untiled / uint8 cases, then per-kernel
 timings on a batch of 1200^2 tile windows.  Writes gpurun_out/ab_pipeline.json.
-Usage: python scripts/ab_pipeline.py [--size 6000] [--variants 0,0 1,1 2,0 0,3 0,2 2,3] [--quick]"""
+Usage: python scripts/ab_pipeline.py [--size 6000] [--variants 0,0 2,0 3,0 0,4 ...] [--quick]"""
 import argparse
 import json
 import os
@@ -29,7 +29,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", type=int, default=6000)
     ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--variants", nargs="*", default=["0,0", "1,1", "2,0", "0,3", "0,2", "2,3"])
+    ap.add_argument("--variants", nargs="*", default=["0,0", "2,0", "3,0", "0,3", "0,4", "2,4", "3,4", "1,1", "0,2"])
     ap.add_argument("--quick", action="store_true", help="parity on the first two cases only")
     args = ap.parse_args()
     variants = [tuple(int(x) for x in v.split(",")) for v in args.variants]
