@@ -40,6 +40,12 @@ extern "C" {
 int ma_version(void);
 const char* ma_last_error(void);
 
+/* Process-wide tuning options (none changes a result).  MA_OPT_NMI_VARIANT: 0 = one pixel per thread with warp-level
+ * aggregation (default), 1 = 16 pixels per thread with run-length merging before the histogram atomics. */
+#define MA_OPT_NMI_VARIANT 0
+#define MA_OPT_COUNT 1
+int ma_set_option(int option, int value);
+
 /* ---- image pyramid: cv.pyrDown (optflow_reg/optflow_registrator.py:194) -------------------
  * dst is ((h+1)/2, (w+1)/2); 5x5 binomial, BORDER_REFLECT_101, (s+128)>>8. dtype MA_U8|MA_U16. */
 int ma_pyrdown(const void* src, size_t src_pitch, int h, int w, int dtype,

@@ -27,6 +27,7 @@ lib = ctypes.CDLL(LIB_PATH)
 PROTOTYPES = {
     "ma_version": (c_int, []),
     "ma_last_error": (c_char_p, []),
+    "ma_set_option": (c_int, [c_int, c_int]),
     "ma_pyrdown": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "ma_pyrdown_rows": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "ma_pyrup_flow": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_float, c_void_p]),
@@ -80,6 +81,12 @@ for _name, (_res, _args) in PROTOTYPES.items():
     _fn = getattr(lib, _name)  # AttributeError here = header and library out of sync
     _fn.restype = _res
     _fn.argtypes = _args
+
+
+# experimental kernel selection from the environment (results are identical in every variant)
+MA_OPT_NMI_VARIANT = 0
+if os.environ.get("MA_NMI_VARIANT", "0") not in ("", "0"):
+    lib.ma_set_option(MA_OPT_NMI_VARIANT, int(os.environ["MA_NMI_VARIANT"]))
 
 
 def check(status: int, what: str):

@@ -18,6 +18,8 @@ static const char* kKernelNames[K_COUNT] = {
     "minmax", "dog_row", "dog_col", "dog_quant", "nmi_hist", "nmi_entropy", "zmip", "norm_u8", "small", "warp_affine"};
 
 static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_options[MA_OPT_COUNT];
+int get_option(int option) { return (option >= 0 && option < MA_OPT_COUNT) ? g_options[option].load(std::memory_order_relaxed) : 0; }
 static std::atomic<int> g_prof_on{0};
 static std::mutex g_prof_mu;
 struct Pending { int id; cudaEvent_t a, b; double units; };
@@ -64,6 +66,11 @@ static void prof_drain() {
 using namespace ma;
 
 extern "C" int ma_version(void) { return 100; }
+extern "C" int ma_set_option(int option, int value) {
+    if (option < 0 || option >= MA_OPT_COUNT) return invalid("ma_set_option: unknown option");
+    g_options[option].store(value);
+    return MA_OK;
+}
 extern "C" const char* ma_last_error(void) { return g_last_error.c_str(); }
 extern "C" long long ma_launch_count(void) { return g_launches.load(); }
 extern "C" int ma_profile_kernels(void) { return K_COUNT; }

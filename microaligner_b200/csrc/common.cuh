@@ -11,6 +11,7 @@
 namespace ma {
 
 void set_error(const std::string& s);
+int get_option(int option);   // ma_set_option values (process-wide), 0 when never set
 int cuda_fail(cudaError_t e, const char* what);
 
 #define MA_CUDA_CHECK(expr)                                   \

@@ -34,6 +34,49 @@ __global__ void __launch_bounds__(256) nmi_hist_kernel(const uint8_t* __restrict
     }
 }
 
+// Experimental variant (ma_set_option(MA_OPT_NMI_VARIANT, 1)): 16 pixels per thread from two 128-bit loads, equal
+// consecutive (a, b) pairs merged in registers before the atomic -- the DoG images the gate compares are smooth, so
+// runs are long -- instead of one byte load per image and a warp-wide match_any per pixel.  Same histogram.
+__global__ void __launch_bounds__(256) nmi_hist_rle_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
+                                                           size_t n, size_t chunk, size_t chunk0, unsigned* __restrict__ hist) {
+    const int slot = blockIdx.y;
+    const size_t beg = (chunk0 + slot) * chunk;
+    const size_t end = beg + chunk < n ? beg + chunk : n;
+    const size_t len = end - beg;
+    unsigned* H = hist + (size_t)slot * 65536;
+    const uint8_t* pa = a + beg;
+    const uint8_t* pb = b + beg;
+    // [0, head) scalar up to the first 16-byte boundary, [head, tail0) as 16-pixel vectors, [tail0, len) scalar;
+    // images whose chunk starts are not equally aligned are processed pixel by pixel
+    const bool vec = ((reinterpret_cast<uintptr_t>(pa) ^ reinterpret_cast<uintptr_t>(pb)) & 15) == 0;
+    size_t head = vec ? ((16 - (reinterpret_cast<uintptr_t>(pa) & 15)) & 15) : len;
+    if (head > len) head = len;
+    const size_t nvec = (len - head) / 16;
+    const size_t tail0 = head + nvec * 16;
+    const size_t gtid = (size_t)blockIdx.x * 256 + threadIdx.x, gsz = (size_t)gridDim.x * 256;
+    for (size_t i = gtid; i < head; i += gsz) atomicAdd(&H[((unsigned)pa[i] << 8) | pb[i]], 1u);
+    for (size_t i = tail0 + gtid; i < len; i += gsz) atomicAdd(&H[((unsigned)pa[i] << 8) | pb[i]], 1u);
+    const uint4* va = reinterpret_cast<const uint4*>(pa + head);
+    const uint4* vb = reinterpret_cast<const uint4*>(pb + head);
+    for (size_t v = gtid; v < nvec; v += gsz) {
+        const uint4 A = __ldg(va + v), B = __ldg(vb + v);
+        const unsigned aw[4] = {A.x, A.y, A.z, A.w}, bw[4] = {B.x, B.y, B.z, B.w};
+        unsigned run = 0, cnt = 0;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const unsigned key = (((aw[q >> 2] >> (8 * (q & 3))) & 255u) << 8) | ((bw[q >> 2] >> (8 * (q & 3))) & 255u);
+            if (cnt != 0 && key == run) {
+                ++cnt;
+            } else {
+                if (cnt != 0) atomicAdd(&H[run], cnt);
+                run = key;
+                cnt = 1;
+            }
+        }
+        atomicAdd(&H[run], cnt);
+    }
+}
+
 __device__ __forceinline__ double block_sum(double v, double* sh) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -136,7 +179,9 @@ extern "C" int ma_nmi_chunk_range(const uint8_t* a, const uint8_t* b, size_t n, 
         int g = (int)std::min<size_t>(kNmiSlots, chunk_end - c0);
         MA_CUDA_CHECK(cudaMemsetAsync(hist, 0, (size_t)g * kHistBytes, s));
         int bpc = (int)std::max<size_t>(1, std::min<size_t>((chunk + 256 * 16 - 1) / (256 * 16), (size_t)(148 * 8 + g - 1) / g));
-        { KernelScope ks(K_NMI_HIST, s, (double)std::min<size_t>(n - c0 * chunk, (size_t)g * chunk)); nmi_hist_kernel<<<dim3(bpc, g), 256, 0, s>>>(a, b, n, chunk, c0, hist); }
+        { KernelScope ks(K_NMI_HIST, s, (double)std::min<size_t>(n - c0 * chunk, (size_t)g * chunk));
+        if (get_option(MA_OPT_NMI_VARIANT) == 1) nmi_hist_rle_kernel<<<dim3(bpc, g), 256, 0, s>>>(a, b, n, chunk, c0, hist);
+        else nmi_hist_kernel<<<dim3(bpc, g), 256, 0, s>>>(a, b, n, chunk, c0, hist); }
         { KernelScope ks(K_NMI_ENTROPY, s, (double)g); nmi_entropy_kernel<<<g, 256, 0, s>>>(hist, n, chunk, c0, scores_out); }
         MA_LAUNCH_CHECK("nmi kernels");
     }
