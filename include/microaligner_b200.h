@@ -126,6 +126,9 @@ int ma_farneback_tiles(const void* mov, const void* ref, size_t pitch, int dtype
  *                                            4 four outputs per thread (three CTAs per SM) */
 #define MA_FB_VARIANT_SHIFT_V 8
 #define MA_FB_VARIANT_SHIFT_H 12
+/*   flags |= p << MA_FB_VARIANT_SHIFT_P   p: 0 polynomial expansion staged through shared memory (default),
+ *                                            1 warp-marching expansion (registers + shuffles, no barriers) */
+#define MA_FB_VARIANT_SHIFT_P 16
 int ma_farneback_tiles_ex(const void* mov, const void* ref, size_t pitch, int dtype, int h, int w,
                           int T, int ov, int win, int iters, int tile_begin, int tile_end,
                           float* flow_out, void* workspace, size_t workspace_bytes, unsigned flags, void* stream);

@@ -212,6 +212,135 @@ __global__ void __launch_bounds__(256) fb_polyexp_kernel(const T* __restrict__ m
 }
 
 // ------------------------------------------------------------------------------------------------
+// K1 experimental variant (flags bits 16..19 = 1): "marching" polynomial expansion without shared memory
+// and without block barriers.  A warp owns a strip of 28 output columns (lanes 2..29; lanes 0, 1, 30, 31
+// carry the halo) and marches down a band of rows: per virtual row v = ya-2 .. yb+1 (actual row
+// REFLECT_101(v)) each lane loads one pixel of both images, the row prefilter takes its neighbours by
+// shuffle (sources follow REFLECT_101 at the tile edge), and the column prefilter, the vertical expansion
+// pass and the row-replication rules work on three-deep rolling registers; the horizontal pass gets T0..T2
+// of the neighbouring (replicated) columns by shuffle.  Arithmetic and its order are those of
+// fb_polyexp_kernel; scripts/emu/polyexp_march.py checks the index logic against the oracle on the CPU.
+// 28/32 lanes produce output and a band re-reads 4 of its PM_BAND rows, but the ~620 instructions per pixel
+// of the staged kernel (index math, five block-wide phases per image) shrink to ~250.
+// ------------------------------------------------------------------------------------------------
+constexpr int PM_OUTW = 28;    // output columns per warp
+constexpr int PM_BAND = 96;    // output rows per warp task
+constexpr int PM_WARPS = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(PM_WARPS * 32) fb_polyexp_march_kernel(const T* __restrict__ mov, const T* __restrict__ ref,
+                                                                          size_t pitch, FbBatch b, const __grid_constant__ FbConsts cst) {
+    const TileGeom& g = b.g;
+    const int Sh = g.Sh, Sw = g.Sw;
+    const int slot = blockIdx.z;
+    const int tile = b.tile0 + slot;
+    const int ti = tile / g.nx, tj = tile % g.nx;
+    const int oy = ti * g.Th - g.ov, ox = tj * g.Tw - g.ov;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int xs = (blockIdx.x * PM_WARPS + warp) * PM_OUTW;
+    if (xs >= Sw) return;                       // warp-uniform; the kernel has no block-wide barrier
+    const int ya = blockIdx.y * PM_BAND, yb = min(ya + PM_BAND, Sh);
+    const int x = xs - 2 + lane;                // this lane's tile column
+    const bool colin = (unsigned)x < (unsigned)Sw;
+    const bool colok = colin && (unsigned)(ox + x) < (unsigned)g.w;
+    // shuffle sources: prefilter neighbours (REFLECT_101 at the tile edge) and expansion neighbours (replicate)
+    int srcL = lane, srcR = lane;
+    if (colin) {
+        srcL = min(max(reflect101(x - 1, Sw) - (xs - 2), 0), 31);
+        srcR = min(max(reflect101(x + 1, Sw) - (xs - 2), 0), 31);
+    }
+    const int tL = min(max(min(max(x - 1, 0), Sw - 1) - (xs - 2), 0), 31);
+    const int tR = min(max(min(max(x + 1, 0), Sw - 1) - (xs - 2), 0), 31);
+    const bool writer = lane >= 2 && lane < 2 + PM_OUTW && colin;
+    const T* pm = mov + (ox + x);
+    const T* pr = ref + (ox + x);
+    auto load = [&](int v, float& a, float& c) {
+        const int gy = oy + reflect101(v, Sh);
+        a = 0.0f;
+        c = 0.0f;
+        if (colok && (unsigned)gy < (unsigned)g.h) {
+            a = (float)__ldg(reinterpret_cast<const T*>(reinterpret_cast<const char*>(pm) + (size_t)gy * pitch));
+            c = (float)__ldg(reinterpret_cast<const T*>(reinterpret_cast<const char*>(pr) + (size_t)gy * pitch));
+        }
+    };
+    float th0[2] = {0, 0}, th1[2] = {0, 0}, th2[2] = {0, 0}, P0[2] = {0, 0}, P1[2] = {0, 0}, P2[2] = {0, 0};
+    float nxt[2];
+    load(ya - 2, nxt[0], nxt[1]);
+    for (int v = ya - 2; v < yb + 2; ++v) {
+        float raw[2] = {nxt[0], nxt[1]};
+        if (v + 1 < yb + 2) load(v + 1, nxt[0], nxt[1]);    // in flight during this row's arithmetic
+#pragma unroll
+        for (int im = 0; im < 2; ++im) {
+            const float l = __shfl_sync(0xffffffffu, raw[im], srcL), r = __shfl_sync(0xffffffffu, raw[im], srcR);
+            th0[im] = th1[im];
+            th1[im] = th2[im];
+            th2[im] = __fadd_rn(__fmul_rn(raw[im], 0.5f), __fmul_rn(__fadd_rn(l, r), 0.25f));
+        }
+        if (v < ya) continue;
+#pragma unroll
+        for (int im = 0; im < 2; ++im) {                     // prefiltered image at virtual row v - 1
+            P0[im] = P1[im];
+            P1[im] = P2[im];
+            P2[im] = __fadd_rn(__fmul_rn(th1[im], 0.5f), __fmul_rn(__fadd_rn(th0[im], th2[im]), 0.25f));
+        }
+        const int y = v - 2;
+        if (y < ya || y >= yb) continue;
+        float R[2][5];
+#pragma unroll
+        for (int im = 0; im < 2; ++im) {
+            const float s0 = y == 0 ? P1[im] : P0[im], sc = P1[im], s1 = y == Sh - 1 ? P1[im] : P2[im];
+            const float pp = __fadd_rn(s0, s1);
+            const float t0 = __fadd_rn(__fmul_rn(sc, cst.g0), __fmul_rn(cst.g1, pp));
+            const float t1 = __fadd_rn(0.0f, __fmul_rn(cst.xg1, __fsub_rn(s1, s0)));
+            const float t2 = __fadd_rn(0.0f, __fmul_rn(cst.xxg1, pp));
+            const float t0l = __shfl_sync(0xffffffffu, t0, tL), t0r = __shfl_sync(0xffffffffu, t0, tR);
+            const float t1l = __shfl_sync(0xffffffffu, t1, tL), t1r = __shfl_sync(0xffffffffu, t1, tR);
+            const float t2l = __shfl_sync(0xffffffffu, t2, tL), t2r = __shfl_sync(0xffffffffu, t2, tR);
+            // horizontal pass: float sums/differences, double accumulation (oracle/farneback_np.py:polyexp)
+            double b1 = (double)__fmul_rn(t0, cst.g0);
+            double b3 = (double)__fmul_rn(t1, cst.g0);
+            double b5 = (double)__fmul_rn(t2, cst.g0);
+            const double tg = (double)__fadd_rn(t0r, t0l);
+            b1 = __dadd_rn(b1, __dmul_rn(tg, (double)cst.g1));
+            const double b4 = __dmul_rn(tg, (double)cst.xxg1);
+            const double b2 = (double)__fmul_rn(__fsub_rn(t0r, t0l), cst.xg1);
+            b3 = __dadd_rn(b3, (double)__fmul_rn(__fadd_rn(t1r, t1l), cst.g1));
+            const double b6 = (double)__fmul_rn(__fsub_rn(t1r, t1l), cst.xg1);
+            b5 = __dadd_rn(b5, (double)__fmul_rn(__fadd_rn(t2r, t2l), cst.g1));
+            R[im][0] = (float)__dmul_rn(b3, cst.ig11);
+            R[im][1] = (float)__dmul_rn(b2, cst.ig11);
+            R[im][2] = (float)__dadd_rn(__dmul_rn(b1, cst.ig03), __dmul_rn(b5, cst.ig33));
+            R[im][3] = (float)__dadd_rn(__dmul_rn(b1, cst.ig03), __dmul_rn(b4, cst.ig33));
+            R[im][4] = (float)__dmul_rn(b6, cst.ig55);
+        }
+        if (!writer) continue;
+        const size_t o = (size_t)y * b.Sp + x;
+        float* __restrict__ R0p = slot_plane(b, slot, 0, 0);
+        float* __restrict__ R1p = slot_plane(b, slot, 1, 0);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            R0p[k * b.plane + o] = R[0][k];
+            R1p[k * b.plane + o] = R[1][k];
+        }
+        // UpdateMatrices with flow == 0: the sample of R1 is R1 itself where (x, y) has a right / lower neighbour
+        float r2, r3, r4, r5, r6;
+        if (x < Sw - 1 && y < Sh - 1) {
+            r2 = R[1][0];
+            r3 = R[1][1];
+            r4 = __fmul_rn(__fadd_rn(R[0][2], R[1][2]), 0.5f);
+            r5 = __fmul_rn(__fadd_rn(R[0][3], R[1][3]), 0.5f);
+            r6 = __fmul_rn(__fadd_rn(R[0][4], R[1][4]), 0.25f);
+        } else {
+            r2 = r3 = 0.0f;
+            r4 = R[0][2];
+            r5 = R[0][3];
+            r6 = __fmul_rn(R[0][4], 0.5f);
+        }
+        finish_matrices(R[0][0], R[0][1], r2, r3, r4, r5, r6, 0.0f, 0.0f, x, y, Sw, Sh, slot_plane(b, slot, 2, 0), b.plane, o);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K2: UpdateMatrices for one pixel (FarnebackUpdateMatrices, all f32, left-to-right sums)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void update_matrices_px(const float* __restrict__ R0, const float* __restrict__ R1,
@@ -1148,7 +1277,8 @@ extern "C" int ma_farneback_tiles_ex(const void* mov, const void* ref, size_t pi
     //      3 CTA per block + register stores, 4 four outputs per thread (3 CTAs per SM)
     int v_var = (flags >> 8) & 15, h_var = (flags >> 12) & 15;
     if (flags & MA_FB_PIPELINED) { if (!v_var) v_var = 1; if (!h_var) h_var = 1; }
-    if (v_var > 3 || h_var > 4) return invalid("ma_farneback_tiles: unknown kernel variant");
+    const int p_var = (flags >> 16) & 15;    // polynomial expansion: 0 staged through shared memory (default), 1 marching warps
+    if (v_var > 3 || h_var > 4 || p_var > 1) return invalid("ma_farneback_tiles: unknown kernel variant");
     const bool pipelined = v_var == 1 || v_var == 3;   // V variants 1 and 3 work on 64-output boxes
     if (!mov || !ref || !flow_out || !workspace || h <= 0 || w <= 0) return invalid("ma_farneback_tiles: bad argument");
     if (dtype != MA_U8 && dtype != MA_U16) return invalid("ma_farneback_tiles: dtype must be MA_U8 or MA_U16");
@@ -1211,11 +1341,19 @@ extern "C" int ma_farneback_tiles_ex(const void* mov, const void* ref, size_t pi
         b.Sp = Sp; b.SpT = SpT; b.plane = plane; b.ws = (float*)workspace;
         double tpx = (double)b.ntiles * g.Sh * g.Sw;
         { KernelScope ks(K_POLYEXP, s, tpx);
-        dim3 pg(ceil_div(g.Sw, PE_BW), ceil_div(g.Sh, PE_BH), b.ntiles);
-        if (dtype == MA_U8)
-            fb_polyexp_kernel<uint8_t><<<pg, 256, 0, s>>>((const uint8_t*)mov, (const uint8_t*)ref, pitch, b, cst);
-        else
-            fb_polyexp_kernel<uint16_t><<<pg, 256, 0, s>>>((const uint16_t*)mov, (const uint16_t*)ref, pitch, b, cst); }
+        if (p_var == 1 && g.Sh >= 8 && g.Sw >= 8) {
+            dim3 pg(ceil_div(ceil_div(g.Sw, PM_OUTW), PM_WARPS), ceil_div(g.Sh, PM_BAND), b.ntiles);
+            if (dtype == MA_U8)
+                fb_polyexp_march_kernel<uint8_t><<<pg, PM_WARPS * 32, 0, s>>>((const uint8_t*)mov, (const uint8_t*)ref, pitch, b, cst);
+            else
+                fb_polyexp_march_kernel<uint16_t><<<pg, PM_WARPS * 32, 0, s>>>((const uint16_t*)mov, (const uint16_t*)ref, pitch, b, cst);
+        } else {
+            dim3 pg(ceil_div(g.Sw, PE_BW), ceil_div(g.Sh, PE_BH), b.ntiles);
+            if (dtype == MA_U8)
+                fb_polyexp_kernel<uint8_t><<<pg, 256, 0, s>>>((const uint8_t*)mov, (const uint8_t*)ref, pitch, b, cst);
+            else
+                fb_polyexp_kernel<uint16_t><<<pg, 256, 0, s>>>((const uint16_t*)mov, (const uint16_t*)ref, pitch, b, cst);
+        } }
         // TMA descriptors over this batch's planes: M as [plane][y][x], V^T as [plane][x][y]
         CUtensorMap mapM, mapVT, mapVT4;
         uint64_t nplanes = (uint64_t)b.ntiles * kSlotPlanes;

@@ -205,7 +205,13 @@ FARNEBACK_WORKSPACE_BUDGET = 24 << 30  # bytes of HBM the tile batch may use
 # window blur as persistent, barrier-free kernels (MA_FB_PIPELINED): same results; experimental, off by default
 FB_PIPELINED = os.environ.get("MA_FB_PIPELINE", "0") not in ("", "0")
 # experimental window-blur kernel variants "v,h" (MA_FB_VARIANT_SHIFT_V / _H in the header); all bit-identical
-FB_VARIANT = tuple(int(x) for x in os.environ.get("MA_FB_VARIANT", "0,0").split(","))
+FB_VARIANT = tuple(int(x) for x in os.environ.get("MA_FB_VARIANT", "0,0,0").split(","))
+
+
+def _variant_bits(variant) -> int:
+    """(v, h[, p]) -> flag bits: V-pass blur << 8, H-pass blur << 12, polynomial expansion << 16."""
+    v = tuple(int(x) for x in variant) + (0, 0, 0)
+    return (v[0] << 8) | (v[1] << 12) | (v[2] << 16)
 
 
 def _fb_workspace(device, nbytes: int) -> torch.Tensor:
@@ -231,7 +237,7 @@ def farneback_tiles(mov: torch.Tensor, ref: torch.Tensor, tile_size: int, overla
     """Stitched flow of the tiled (tile_size > 0) or untiled (tile_size <= 0) Farneback.
     contract_fma=True trades bit parity for speed in the window blur (MA_FB_CONTRACT_FMA).
     pipelined selects the persistent window-blur kernels (MA_FB_PIPELINED, same results); None = FB_PIPELINED.
-    variant = (v, h) picks experimental window-blur kernels per pass (include/microaligner_b200.h); None = FB_VARIANT."""
+    variant = (v, h[, p]) picks experimental kernels per stage (include/microaligner_b200.h); None = FB_VARIANT."""
     _req(mov, "moving image")
     _req(ref, "reference image")
     if mov.shape != ref.shape or mov.dtype != ref.dtype:
@@ -250,7 +256,7 @@ def farneback_tiles(mov: torch.Tensor, ref: torch.Tensor, tile_size: int, overla
     check(lib.ma_farneback_tiles_ex(mov.data_ptr(), ref.data_ptr(), w * es, _code(ref), h, w, T, int(overlap), int(win),
                                     int(iters), int(t0), int(t1), out.data_ptr(), ws.data_ptr(), ws.numel(),
                                     (1 if contract_fma else 0) | (2 if (FB_PIPELINED if pipelined is None else pipelined) else 0)
-                                    | (int((variant or FB_VARIANT)[0]) << 8) | (int((variant or FB_VARIANT)[1]) << 12),
+                                    | _variant_bits(variant or FB_VARIANT),
                                     _stream()), "ma_farneback_tiles")
     return out
 

@@ -1,7 +1,7 @@
-"""A/B of the window-blur kernel variants (include/microaligner_b200.h, MA_FB_VARIANT_SHIFT_V / _H): bit-identity of
+"""A/B of the Farneback kernel variants (include/microaligner_b200.h, MA_FB_VARIANT_SHIFT_V / _H / _P): bit-identity of
 the stitched flow against the default kernels over ragged / small-window / untiled / uint8 cases, then per-kernel
 timings on a batch of 1200^2 tile windows.  Writes gpurun_out/ab_pipeline.json.
-Usage: python scripts/ab_pipeline.py [--size 6000] [--variants 0,0 2,0 3,0 0,4 ...] [--quick]"""
+Usage: python scripts/ab_pipeline.py [--size 6000] [--variants 0,0,0 0,0,1 2,4,1 ...]  (v,h,p) [--quick]"""
 import argparse
 import json
 import os
@@ -29,7 +29,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", type=int, default=6000)
     ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--variants", nargs="*", default=["0,0", "2,0", "3,0", "0,3", "0,4", "2,4", "3,4", "1,1", "0,2"])
+    ap.add_argument("--variants", nargs="*", default=["0,0,0", "0,0,1", "2,0,0", "3,0,0", "0,3,0", "0,4,0", "2,4,1", "3,4,1", "1,1,0", "0,2,0"])
     ap.add_argument("--quick", action="store_true", help="parity on the first two cases only")
     args = ap.parse_args()
     variants = [tuple(int(x) for x in v.split(",")) for v in args.variants]
@@ -42,11 +42,11 @@ def main():
         ref, mov = synth_pair(h, w, 7, dt)
         dref, dmov = ops.to_device(ref), ops.to_device(mov)
         win = ov - (1 - ov % 2) if T > 0 else 99
-        base = ops.farneback_tiles(dmov, dref, T, ov, win, it, contract_fma=contract, pipelined=False, variant=(0, 0))
+        base = ops.farneback_tiles(dmov, dref, T, ov, win, it, contract_fma=contract, pipelined=False, variant=(0, 0, 0))
         for v in variants:
-            if v == (0, 0):
+            if not any(v):
                 continue
-            key = f"{v[0]},{v[1]} | {name}"
+            key = f"{','.join(map(str, v))} | {name}"
             try:
                 out = ops.farneback_tiles(dmov, dref, T, ov, win, it, contract_fma=contract, pipelined=False, variant=v)
                 torch.cuda.synchronize()
@@ -63,7 +63,7 @@ def main():
                 break
         if "aborted" in res:
             break
-    res["identical_variants"] = sorted(f"{v[0]},{v[1]}" for v in good)
+    res["identical_variants"] = sorted(",".join(map(str, v)) for v in good)
     res["parity_seconds"] = time.time() - t_start
 
     if "aborted" not in res:
@@ -87,8 +87,8 @@ def main():
                 e1.record()
                 torch.cuda.synchronize()
                 _lib.lib.ma_profile_enable(0)
-                prof = {k: round(v_[0] / args.reps, 3) for k, v_ in _lib.profile_summary().items() if k.startswith("fb_blur")}
-                key = f"{v[0]},{v[1]}{' contract_fma' if contract else ''}"
+                prof = {k: round(v_[0] / args.reps, 3) for k, v_ in _lib.profile_summary().items() if k.startswith("fb_")}
+                key = f"{','.join(map(str, v))}{' contract_fma' if contract else ''}"
                 res["timing"][key] = {"ms_per_call": round(e0.elapsed_time(e1) / args.reps, 3), **prof}
                 print(key, res["timing"][key], flush=True)
     res["seconds"] = time.time() - t_start
