@@ -11,6 +11,7 @@ rectangle exchanges.  Global scalars -- DoG min/max and the per-chunk NMI scores
 Levels the reference computes untiled (max(shape)/tile_size < 2) are tiny and run replicated.
 With one rank every exchange is a no-op and the code below is simply the single-GPU path."""
 import contextlib
+import os
 import time
 from collections import defaultdict
 from math import log2
@@ -75,6 +76,23 @@ class LevelLayout:
     def fb_rects(self):
         return [parallel.tile_range_rects(t, self.nx, self.T, self.h, self.w) for t in self.fb_tiles]
 
+    def input_rows(self, use_dog: bool) -> Range:
+        """Rows of this level's ref / mov pyramid images that THIS rank ever reads in Engine.register(): its band with
+        the tile-window overlap (pre-/post-warp), the NMI chunk overrun and the 20-row DoG halo of the gate, and the
+        tile windows of its Farneback tiles (+ DoG halo when the flow runs on DoG images); a few spare rows on top.
+        An unsharded level is read completely."""
+        if not self.sharded:
+            return (0, self.h)
+        over = -(-self.T * self.T // self.w) + 1
+        a, b = self.band
+        need = None
+        if b > a:
+            need = _clip(a - self.ov - 24, b + max(self.ov, over + 20) + 24, self.h)
+        fa, fb = self.fb_window_rows(24 if use_dog else 4)[self.rank]
+        if fb > fa:
+            need = (fa, fb) if need is None else _union(need, (fa, fb))
+        return need if need is not None else (0, 0)
+
 
 class Engine:
     def __init__(self, tile_size=1000, overlap=100, num_pyr_lvl=4, num_iterations=3, use_full_res_img=False,
@@ -93,6 +111,10 @@ class Engine:
         self.decisions: List[dict] = []
         self.force_decisions = None  # test hook (list of bools per level), mirrors oracle.reference_flow.register
         self.gather_flow = True      # False: with several ranks the returned flow is valid on this rank's band only
+        # opt-in (MA_LOCAL_PYRAMID=1), several ranks only: every rank reduces just the rows of each pyramid level it
+        # will read (LevelLayout.input_rows) from its replicated copy of the input, instead of computing a slice of
+        # every level and gathering the levels over NVLink.  Rows outside that range stay uninitialised.
+        self.local_pyramid = os.environ.get("MA_LOCAL_PYRAMID", "0") not in ("", "0")
         self.flow_layout = None
 
     def log(self, *a):
@@ -143,6 +165,43 @@ class Engine:
             pyr.append(arr)
             factors.append(1)
         return pyr, factors
+
+    def level_shapes(self, shape) -> List[Tuple[int, int]]:
+        """Shapes of the pyrDown chain in generation order (fine -> coarse), with pyramid()'s stopping rule."""
+        out, (h, w) = [], shape
+        for lvl in range(self.num_pyr_lvl):
+            factor = 2 ** (lvl + 1)
+            if shape[0] / factor < 100 or shape[1] / factor < 100:
+                break
+            h, w = (h + 1) // 2, (w + 1) // 2
+            out.append((h, w))
+        return out
+
+    @staticmethod
+    def pyramid_requirements(need: Sequence[Range], heights: Sequence[int]) -> List[Range]:
+        """need[k] = rows of level k (generation order, fine -> coarse) a rank reads itself; result[k] = rows it has to
+        COMPUTE: its own plus the rows the 5-tap pyrDown of the next coarser level's requirement reaches (2a-2 .. 2b+1)."""
+        req = list(need)
+        for k in range(len(need) - 2, -1, -1):
+            a, b = req[k + 1]
+            if b > a:
+                sup = _clip(2 * a - 2, 2 * b + 2, heights[k])
+                req[k] = sup if req[k][1] <= req[k][0] else _union(req[k], sup)
+        return req
+
+    def pyramid_local(self, arr: torch.Tensor, shapes, req: Sequence[Range]):
+        """pyramid() for one rank of several: level k holds valid data on rows req[k] only."""
+        pyr, cur = [], arr
+        for (h, w), rows in zip(shapes, req):
+            nxt = torch.empty((h, w), dtype=arr.dtype, device=arr.device)
+            if rows[1] > rows[0]:
+                ops.pyr_down_rows(cur, rows, nxt)
+            pyr.append(nxt)
+            cur = nxt
+        pyr.reverse()
+        if self.full_res:
+            pyr.append(arr)
+        return pyr
 
     def dog_batch(self, items, L: LevelLayout) -> List[torch.Tensor]:
         """uint8 DoG of several images of one level: items = [(img, rows)], result i valid on rows_i.
@@ -197,10 +256,19 @@ class Engine:
     # ------------------------------------------------------------------ register()
     def register(self, ref: torch.Tensor, mov: torch.Tensor) -> torch.Tensor:
         comm, T, ov = self.comm, self.T, self.ov
-        with self.phase("pyramid"):
-            ref_pyr, factors = self.pyramid(ref)
-            mov_pyr, _ = self.pyramid(mov)
         full = LevelLayout(ref.shape[0], ref.shape[1], T, ov, comm)
+        with self.phase("pyramid"):
+            if self.local_pyramid and comm.world > 1:
+                shapes = self.level_shapes(tuple(ref.shape))
+                gen = [LevelLayout(h, w, T, ov, comm) for h, w in shapes]          # fine -> coarse
+                req = self.pyramid_requirements([L.input_rows(self.use_dog) for L in gen], [h for h, _ in shapes])
+                if self.num_pyr_lvl < 0 or (not shapes and not self.full_res):
+                    self.pyramid(ref)                                               # raises the reference's ValueErrors
+                ref_pyr, mov_pyr = self.pyramid_local(ref, shapes, req), self.pyramid_local(mov, shapes, req)
+                factors = [2 ** (k + 1) for k in range(len(shapes))][::-1] + ([1] if self.full_res else [])
+            else:
+                ref_pyr, factors = self.pyramid(ref)
+                mov_pyr, _ = self.pyramid(mov)
         layouts = [LevelLayout(p.shape[0], p.shape[1], T, ov, comm) for p in ref_pyr]
         num_lvl = len(factors)
         self.decisions = []

@@ -20,6 +20,9 @@ CASES = [
     ((700, 820), np.uint16, dict(num_pyr_lvl=2, tile_size=150, overlap=20, use_full_res_img=True, use_dog=True, num_iterations=2)),
     ((640, 530), np.uint8, dict(num_pyr_lvl=2, tile_size=120, overlap=16, use_full_res_img=False, num_iterations=1)),
 ]
+# every pyramid level tiled (>= 2 tiles per side), so that a band-local pyramid really leaves rows uncomputed
+LOCAL_CASE = ((1300, 1500), np.uint16, dict(num_pyr_lvl=2, tile_size=150, overlap=20, use_full_res_img=True, use_dog=True,
+                                            num_iterations=1))
 
 
 def _run(ref, mov, kw):
@@ -36,13 +39,15 @@ def _run(ref, mov, kw):
     return flow.cpu().numpy(), w.warp().cpu().numpy(), [d["better"] for d in reg.decisions]
 
 
-def _worker(rank, world, port, case_id, tmp):
+def _worker(rank, world, port, case_id, tmp, local_pyramid=False):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    if local_pyramid:
+        os.environ["MA_LOCAL_PYRAMID"] = "1"    # read by Engine.__init__
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from microaligner_b200 import parallel
     parallel.init(dist.group.WORLD)
     try:
-        shape, dtype, kw = CASES[case_id]
+        shape, dtype, kw = LOCAL_CASE if case_id < 0 else CASES[case_id]
         ref, mov = synth_pair(shape[0], shape[1], 7, dtype)
         flow, img, dec = _run(ref, mov, kw)
         np.savez(os.path.join(tmp, f"r{rank}.npz"), flow=flow, img=img, dec=np.array(dec))
@@ -65,6 +70,21 @@ def test_sharded_equals_single(cuda, tmp_path, case_id, world):
     ref, mov = synth_pair(shape[0], shape[1], 7, dtype)
     want_flow, want_img, want_dec = _run(ref, mov, kw)
     mp.spawn(_worker, args=(world, _free_port(), case_id, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        got = np.load(tmp_path / f"r{r}.npz")
+        assert list(got["dec"]) == want_dec
+        assert np.array_equal(got["flow"], want_flow), f"rank {r}: flow differs"
+        assert np.array_equal(got["img"], want_img), f"rank {r}: warped image differs"
+
+
+@pytest.mark.xfail(strict=False, reason="opt-in band-local pyramid (MA_LOCAL_PYRAMID=1): written after the round-1 GPU budget "
+                                        "was spent, not yet run on hardware")
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_local_pyramid_equals_single(cuda, tmp_path, world):
+    shape, dtype, kw = LOCAL_CASE
+    ref, mov = synth_pair(shape[0], shape[1], 7, dtype)
+    want_flow, want_img, want_dec = _run(ref, mov, kw)
+    mp.spawn(_worker, args=(world, _free_port(), -1, str(tmp_path), True), nprocs=world, join=True)
     for r in range(world):
         got = np.load(tmp_path / f"r{r}.npz")
         assert list(got["dec"]) == want_dec

@@ -42,3 +42,43 @@ def test_level_layout(h, w, T, ov, world):
         else:
             assert gb == ga
     assert all(l.band == L.bands[r] for r, l in enumerate(layouts))
+
+
+@pytest.mark.parametrize("shape,T,ov,world,use_dog", [((50000, 50000), 1000, 100, 8, False), ((20000, 20000), 1000, 100, 8, True),
+                                                      ((5000, 5300), 1000, 100, 4, False), ((2300, 2100), 300, 40, 3, True),
+                                                      ((1500, 1700), 150, 20, 5, False)])
+def test_local_pyramid_requirements(shape, T, ov, world, use_dog):
+    """Band-local pyramid (Engine.local_pyramid): what a rank computes of every level covers what it reads of that
+    level and what the 5-tap pyrDown of the next coarser level reaches; unsharded levels are complete."""
+    from microaligner_b200.engine import Engine
+    for rank in range(world):
+        comm = FakeComm(rank, world)
+        eng = Engine.__new__(Engine)
+        eng.num_pyr_lvl = 4
+        shapes = eng.level_shapes(shape)
+        assert shapes[0] == ((shape[0] + 1) // 2, (shape[1] + 1) // 2) and len(shapes) <= 4
+        gen = [LevelLayout(h, w, T, ov, comm) for h, w in shapes]
+        need = [L.input_rows(use_dog) for L in gen]
+        req = Engine.pyramid_requirements(need, [h for h, _ in shapes])
+        for k, L in enumerate(gen):
+            a, b = req[k]
+            na, nb = need[k]
+            assert 0 <= a <= b <= L.h
+            if nb > na:
+                assert a <= na and b >= nb
+            if not L.sharded:
+                assert (a, b) == (0, L.h)
+            else:   # the rows every stage of register() reads on a sharded level (engine.py)
+                B = L.band
+                over = -(-T * T // L.w) + 1
+                reads = []
+                if B[1] > B[0]:
+                    reads += [(B[0] - ov, B[1] + ov), (B[0] - 20, B[1] + over + 20)]
+                f = L.fb_window_rows(20 if use_dog else 0)[rank]
+                if f[1] > f[0]:
+                    reads.append(f)
+                for ra, rb in reads:
+                    assert a <= max(ra, 0) and b >= min(rb, L.h)
+            if k + 1 < len(gen) and req[k + 1][1] > req[k + 1][0]:
+                ca, cb = req[k + 1]
+                assert a <= max(2 * ca - 2, 0) and b >= min(2 * cb + 2, L.h)
