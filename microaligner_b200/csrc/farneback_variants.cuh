@@ -17,7 +17,7 @@ namespace ma {
 // shuffle (sources follow REFLECT_101 at the tile edge), and the column prefilter, the vertical expansion
 // pass and the row-replication rules work on three-deep rolling registers; the horizontal pass gets T0..T2
 // of the neighbouring (replicated) columns by shuffle.  Arithmetic and its order are those of
-// fb_polyexp_kernel; scripts/emu/polyexp_march.py checks the index logic against the oracle on the CPU.
+// fb_polyexp_kernel; tests/emu_polyexp_march.py checks the index logic against the oracle on the CPU.
 // 28/32 lanes produce output and a band re-reads 4 of its PM_BAND rows, but the ~620 instructions per pixel
 // of the staged kernel (index math, five block-wide phases per image) shrink to ~250.
 // ------------------------------------------------------------------------------------------------

@@ -1,13 +1,13 @@
 """CPU emulation (numpy, lanes as a vector of 32) of the warp-marching polynomial-expansion kernel
 (fb_polyexp_march_kernel): validates the index logic -- virtual rows with REFLECT_101, rolling windows, edge selects,
 shuffle source lanes -- bit-exactly against oracle.farneback_np.polyexp(prefilter3(window)).
-Run: python scripts/emu/polyexp_march.py"""
+Test infrastructure (imports the oracle); driven by tests/test_emu_cpu.py, or run it directly."""
 import os
 import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import farneback_np as fb  # noqa: E402
 
 F32, F64 = np.float32, np.float64
