@@ -15,6 +15,7 @@
 //   * second normalise: a = float(255*(1/(dmax-dmin))), b = float(-dmin*scale), u8 = sat(rint(fmaf(d,a,b)))
 // Both global reductions stay on the device (ordered-key atomicMin/Max); nothing syncs with the host.
 #include <cmath>
+#include <atomic>
 #include "common.cuh"
 #include "packed.cuh"
 #include "tma.cuh"
@@ -432,9 +433,7 @@ extern "C" int ma_dog_diff_rows(const void* src, size_t src_pitch, int dtype, in
     const int ra = std::max(row_begin - 20, 0), rb = std::min(row_end + 20, h);   // rows the row pass produces
     float* A5 = (float*)((char*)workspace + 256);
     float* A9 = A5 + (size_t)(rb - ra) * wp;
-    static DogTaps taps;
-    static bool taps_ready = false;
-    if (!taps_ready) { make_dog_taps(taps); taps_ready = true; }
+    static const DogTaps taps = [] { DogTaps t; make_dog_taps(t); return t; }();   // thread-safe one-time init
     { KernelScope ks(K_SMALL, s); init_minmax_keys<<<1, 32, 0, s>>>(keys, 1); }
     if (row_begin < row_end) {
         double px = (double)(row_end - row_begin) * w;
@@ -448,7 +447,7 @@ extern "C" int ma_dog_diff_rows(const void* src, size_t src_pitch, int dtype, in
             set_error("ma_dog_diff_rows: cuTensorMapEncodeTiled failed");
             return MA_ERR_CUDA;
         }
-        static bool attr_set[64] = {false};  // per device
+        static std::atomic<bool> attr_set[64];  // per device; setting the attribute twice is harmless
         int dev_id = 0;
         cudaGetDevice(&dev_id);
         if (dev_id < 0 || dev_id >= 64 || !attr_set[dev_id]) {

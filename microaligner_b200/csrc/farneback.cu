@@ -21,6 +21,7 @@
 // bound.  Inputs arrive by TMA box loads (zero fill outside the plane, edge rows replicated in shared
 // memory afterwards); each thread keeps 8 packed (f32x2) outputs and two 8-deep packed sliding windows
 // in registers, so shared-memory traffic is 2 LDS.64 per 24 packed FP instructions.
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <vector>
@@ -646,7 +647,7 @@ extern "C" int ma_farneback_tiles_ex(const void* mov, const void* ref, size_t pi
     const size_t pipe_smem = (size_t)kPipeStages * (kStep + 2 * m) * kRowF * sizeof(float);
     const size_t v_smem = std::max((size_t)(vout + 2 * m) * kRowF * sizeof(float), (size_t)kRowF * (vout + 1) * sizeof(float));
     const size_t h_smem = std::max((size_t)2 * (kStep + 2 * m) * kRowF * sizeof(float), (size_t)kStep * kFlowPitch * sizeof(float2));
-    static bool attr_set[64] = {false};  // per device
+    static std::atomic<bool> attr_set[64];  // per device; setting the attributes twice is harmless
     int dev_id = 0;
     cudaGetDevice(&dev_id);
     if (dev_id < 0 || dev_id >= 64 || !attr_set[dev_id]) {
