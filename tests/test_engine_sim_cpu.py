@@ -49,19 +49,19 @@ class _PoisonTorch:
         return self._poison(torch.empty_like(*a, **k))
 
 
-def _run(ref, mov, kw, local_pyramid=False):
+def _run(ref, mov, kw, local_pyramid=False, corrected=False):
     from microaligner_b200 import engine, parallel
     from tests import mock_ops
     engine.ops, engine.torch = mock_ops, _PoisonTorch()
     eng = engine.Engine(kw["tile_size"], kw["overlap"], kw["num_pyr_lvl"], kw["num_iterations"], kw["use_full_res_img"],
-                        kw["use_dog"], comm=parallel.get(), log=lambda *a: None)
+                        kw["use_dog"], comm=parallel.get(), log=lambda *a: None, corrected=corrected)
     eng.local_pyramid = local_pyramid
     flow = eng.register(torch.from_numpy(ref), torch.from_numpy(mov))
     img = eng.warp(torch.from_numpy(mov), flow)
     return flow.numpy().copy(), img.numpy().copy(), [d["better"] for d in eng.decisions]
 
 
-def _worker(rank, world, port, case, tmp, local_pyramid):
+def _worker(rank, world, port, case, tmp, local_pyramid, corrected=False):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from microaligner_b200 import parallel
@@ -69,7 +69,7 @@ def _worker(rank, world, port, case, tmp, local_pyramid):
     try:
         shape, dtype, kw = CASES[case]
         ref, mov = synth_pair(shape[0], shape[1], 3, dtype, amp=2.0, period=160.0)
-        flow, img, dec = _run(ref, mov, kw, local_pyramid)
+        flow, img, dec = _run(ref, mov, kw, local_pyramid, corrected)
         np.savez(os.path.join(tmp, f"r{rank}.npz"), flow=flow, img=img, dec=np.array(dec))
     finally:
         dist.destroy_process_group()
@@ -98,3 +98,17 @@ def test_sharded_engine_equals_single_rank(tmp_path, case, world, local_pyramid)
         assert list(got["dec"]) == want_dec
         assert np.array_equal(got["flow"], want_flow), f"rank {r}: flow differs on {np.count_nonzero(got['flow'] != want_flow)} values"
         assert np.array_equal(got["img"], want_img), f"rank {r}: warped image differs"
+
+
+@pytest.mark.parametrize("world,case,corrected", [(5, "mixed levels", False), (2, "tiled levels, dog", True)])
+def test_sharded_engine_corner_cases(tmp_path, world, case, corrected):
+    """More ranks than tile rows (some ranks own no band at some levels); the opt-in corrected flow composition, which
+    gathers the accumulated flow before composing."""
+    shape, dtype, kw = CASES[case]
+    ref, mov = synth_pair(shape[0], shape[1], 3, dtype, amp=2.0, period=160.0)
+    want_flow, want_img, want_dec = _run(ref, mov, kw, corrected=corrected)
+    mp.spawn(_worker, args=(world, _free_port(), case, str(tmp_path), False, corrected), nprocs=world, join=True)
+    for r in range(world):
+        got = np.load(tmp_path / f"r{r}.npz")
+        assert list(got["dec"]) == want_dec
+        assert np.array_equal(got["flow"], want_flow) and np.array_equal(got["img"], want_img), f"rank {r} differs"
