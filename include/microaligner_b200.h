@@ -43,7 +43,9 @@ const char* ma_last_error(void);
 /* Process-wide tuning options (none changes a result).  MA_OPT_NMI_VARIANT: 0 = one pixel per thread with warp-level
  * aggregation (default), 1 = 16 pixels per thread with run-length merging before the histogram atomics. */
 #define MA_OPT_NMI_VARIANT 0
-#define MA_OPT_COUNT 1
+/* MA_OPT_MINMAX_VARIANT: 0 = row loop (default), 1 = flat 4x-unrolled scan of dense, 16-byte aligned images. */
+#define MA_OPT_MINMAX_VARIANT 1
+#define MA_OPT_COUNT 2
 int ma_set_option(int option, int value);
 
 /* ---- image pyramid: cv.pyrDown (optflow_reg/optflow_registrator.py:194) -------------------

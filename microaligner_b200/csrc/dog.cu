@@ -113,6 +113,33 @@ __global__ void __launch_bounds__(256) minmax_kernel(const T* __restrict__ src, 
     block_minmax_commit(lo, hi, keys);
 }
 
+// Experimental variant (ma_set_option(MA_OPT_MINMAX_VARIANT, 1)) for dense images (pitch == row bytes, 16-byte aligned
+// base): the image as one flat array, four independent 16-byte loads in flight per thread and a grid of a few CTAs per
+// SM, instead of a row loop that leaves each thread one or two loads per row.  min / max are order-independent.
+template <typename T>
+__global__ void __launch_bounds__(256) minmax_flat_kernel(const T* __restrict__ src, size_t n, unsigned* keys) {
+    constexpr int V = 16 / sizeof(T);
+    const size_t nvec = n / V;
+    const uint4* vp = reinterpret_cast<const uint4*>(src);
+    float lo = INFINITY, hi = -INFINITY;
+    const size_t stride = (size_t)gridDim.x * 256;
+    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    for (; i + 3 * stride < nvec; i += 4 * stride) {
+        const uint4 a = __ldg(vp + i), b = __ldg(vp + i + stride), c = __ldg(vp + i + 2 * stride), d = __ldg(vp + i + 3 * stride);
+        minmax_accum16<T>(a, lo, hi);
+        minmax_accum16<T>(b, lo, hi);
+        minmax_accum16<T>(c, lo, hi);
+        minmax_accum16<T>(d, lo, hi);
+    }
+    for (; i < nvec; i += stride) minmax_accum16<T>(__ldg(vp + i), lo, hi);
+    for (size_t t = nvec * V + (size_t)blockIdx.x * 256 + threadIdx.x; t < n; t += stride) {
+        const float v = (float)__ldg(src + t);
+        lo = fminf(lo, v);
+        hi = fmaxf(hi, v);
+    }
+    block_minmax_commit(lo, hi, keys);
+}
+
 __global__ void keys_to_float_kernel(const unsigned* keys, float* out2) {
     out2[0] = key2f(keys[0]);
     out2[1] = key2f(keys[1]);
@@ -397,6 +424,19 @@ extern "C" int ma_minmax(const void* src, size_t pitch, int dtype, int h, int w,
     unsigned* keys = (unsigned*)out2;
     { KernelScope ks(K_SMALL, s); init_minmax_keys<<<1, 32, 0, s>>>(keys, 1); }
     dim3 grid(std::min(ceil_div(w, 256), 8), std::min(h, 1184));
+    const size_t esz = dtype == MA_U8 ? 1 : dtype == MA_U16 ? 2 : 4;
+    if (get_option(MA_OPT_MINMAX_VARIANT) == 1 && (dtype == MA_U8 || dtype == MA_U16 || dtype == MA_F32) &&
+        pitch == (size_t)w * esz && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const size_t n = (size_t)h * w;
+        const int blocks = (int)std::max<size_t>(1, std::min<size_t>(148 * 8, (n * esz / 16 + 1023) / 1024));
+        { KernelScope ks(K_MINMAX, s, (double)n);
+        if (dtype == MA_U8) minmax_flat_kernel<uint8_t><<<blocks, 256, 0, s>>>((const uint8_t*)src, n, keys);
+        else if (dtype == MA_U16) minmax_flat_kernel<uint16_t><<<blocks, 256, 0, s>>>((const uint16_t*)src, n, keys);
+        else minmax_flat_kernel<float><<<blocks, 256, 0, s>>>((const float*)src, n, keys); }
+        { KernelScope ks(K_SMALL, s); keys_to_float_kernel<<<1, 1, 0, s>>>(keys, out2); }
+        MA_LAUNCH_CHECK("minmax_flat_kernel");
+        return MA_OK;
+    }
     { KernelScope ks(K_MINMAX, s, (double)h * w);
     if (dtype == MA_U8) minmax_kernel<uint8_t><<<grid, 256, 0, s>>>((const uint8_t*)src, pitch, h, w, keys);
     else if (dtype == MA_U16) minmax_kernel<uint16_t><<<grid, 256, 0, s>>>((const uint16_t*)src, pitch, h, w, keys);

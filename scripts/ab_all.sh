@@ -23,5 +23,5 @@ except Exception as e:  # noqa: BLE001
     print(v, "failed:", e)
 PY
 done
-MA_NMI_VARIANT=1 MA_FB_VARIANT=2,4,1 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_variant_all.json 2> gpurun_out/bench_variant_all.err
+MA_NMI_VARIANT=1 MA_MINMAX_VARIANT=1 MA_FB_VARIANT=2,4,1 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_variant_all.json 2> gpurun_out/bench_variant_all.err
 tail -c 600 gpurun_out/bench_variant_all.json

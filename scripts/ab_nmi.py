@@ -1,4 +1,4 @@
-"""A/B of the NMI joint-histogram kernels (ma_set_option(MA_OPT_NMI_VARIANT, v)): identical per-chunk scores and
+"""A/B of the NMI joint-histogram kernels and the min / max scan (ma_set_option(MA_OPT_NMI_VARIANT, v)): identical per-chunk scores and
 timings on DoG-like (smooth) and noise-like u8 images.  Usage: python scripts/ab_nmi.py [--size 12000]"""
 import argparse
 import json
@@ -48,6 +48,25 @@ def main():
                                          "identical_scores": bool(torch.equal(ref, scores))}
             print(name, variant, res[f"{name} v{variant}"], flush=True)
     _lib.lib.ma_set_option(_lib.MA_OPT_NMI_VARIANT, 0)
+    # min / max scan variants (ma_set_option(MA_OPT_MINMAX_VARIANT, v)) on a 16-bit image
+    img = (smooth * 65535).to(torch.int32).to(torch.uint16)
+    ref = None
+    for variant in (0, 1):
+        _lib.lib.ma_set_option(_lib.MA_OPT_MINMAX_VARIANT, variant)
+        mm = ops.minmax(img)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.reps):
+            ops.minmax(img)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.reps
+        ref = mm if ref is None else ref
+        res[f"minmax u16 v{variant}"] = {"ms": round(ms, 3), "gb_s": round(img.numel() * 2 / ms / 1e6, 1),
+                                         "identical": bool(torch.equal(ref, mm))}
+        print("minmax", variant, res[f"minmax u16 v{variant}"], flush=True)
+    _lib.lib.ma_set_option(_lib.MA_OPT_MINMAX_VARIANT, 0)
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/ab_nmi.json", "w") as f:
         json.dump(res, f, indent=1)
