@@ -52,3 +52,15 @@ def test_host_api_surface():
     assert r.mov_img is a  # the reference's getter quirk (optflow_registrator.py:72-74)
     assert r.get_dog_sigmas(1) == (5, 9) and r.get_dog_sigmas(32) == (1, 2)
     assert r.dog(a, False) is a
+
+
+def test_variant_flag_bits_and_options():
+    """Experimental-kernel selectors: (v, h, p) -> flag bits of ma_farneback_tiles_ex; ma_set_option validates its index."""
+    from microaligner_b200 import _lib, ops
+    assert ops._variant_bits((0, 0, 0)) == 0 and ops._variant_bits((0, 0)) == 0
+    assert ops._variant_bits((2, 4, 1)) == (2 << 8) | (4 << 12) | (1 << 16)
+    assert ops._variant_bits((1, 1)) == (1 << 8) | (1 << 12)
+    assert ops.FB_VARIANT == (0, 0, 0) or "MA_FB_VARIANT" in __import__("os").environ
+    assert _lib.lib.ma_set_option(_lib.MA_OPT_NMI_VARIANT, 0) == 0
+    assert _lib.lib.ma_set_option(_lib.MA_OPT_MINMAX_VARIANT, 0) == 0
+    assert _lib.lib.ma_set_option(99, 1) != 0
