@@ -6,7 +6,7 @@ import sys
 ROOT = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(ROOT, "microaligner_b200", "csrc")
 OUT = os.path.join(ROOT, "microaligner_b200", "libmicroaligner_b200.so")
-SOURCES = ["api.cu", "warp.cu", "pyramid.cu", "farneback.cu", "dog.cu", "nmi.cu"]
+SOURCES = ["api.cu", "warp.cu", "pyramid.cu", "farneback.cu", "dog.cu", "nmi.cu", "hostcodec.cu"]
 # -fmad=false: never contract a*b+c -- bit parity with OpenCV's SSE-baseline arithmetic depends on it;
 # every fused multiply-add in the tree is an explicit intrinsic.
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",

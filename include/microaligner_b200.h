@@ -190,6 +190,11 @@ void ma_profile_enable(int on);
 void ma_profile_reset(void);
 int ma_profile_read(int id, double* total_ms, long long* launches, double* units);
 
+/* ---- host-side helper of the TIFF page reader (no CUDA): TIFF-flavoured LZW (MSB-first 9..12-bit codes, early
+ * change), `n` compressed bytes -> at most `cap` bytes at dst.  Returns the bytes written, -1 on a corrupt stream.
+ * Replaces what tifffile (utils.py:69-72 `TiffFile.pages[i].asarray()`) delegates to its compiled codec extension. */
+long long ma_tiff_lzw_decode(const uint8_t* src, size_t n, uint8_t* dst, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,6 +58,7 @@ PROTOTYPES = {
     "ma_zmip_normalize_u8": (c_int, [ctypes.POINTER(c_void_p), c_int, c_size_t, c_int, c_int, c_int, c_void_p, c_size_t,
                                      c_void_p, c_void_p]),
     "ma_minmax": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "ma_tiff_lzw_decode": (ctypes.c_longlong, [c_char_p, c_size_t, c_void_p, c_size_t]),
     "ma_launch_count": (ctypes.c_longlong, []),
     "ma_profile_kernels": (c_int, []),
     "ma_profile_kernel_name": (c_char_p, [c_int]),

@@ -189,3 +189,22 @@ def test_page_provider_and_sink(tmp_path):
     prov.close()
     with tiffio.TiffFile(tmp_path / "out.tif") as tif:
         assert np.array_equal(tif.asarray().reshape(4, 50, 70), np.stack(a))
+
+
+def test_native_lzw_decoder_matches_python_and_rejects_garbage(tmp_path):
+    """ma_tiff_lzw_decode (host code in the shared library) against the pure-Python decoder on a libtiff-written strip."""
+    rng = np.random.default_rng(9)
+    a = (np.add.outer(np.arange(64), np.arange(300)) + rng.integers(0, 3, (64, 300))).astype(np.uint16)
+    p = tmp_path / "l.tif"
+    PIL.fromarray(a).save(p, compression="tiff_lzw")
+    with tiffio.TiffFile(p) as tif:
+        pg = tif.pages[0]
+        off, n, y0, x0, rows, cols = pg.segments[0]
+        raw, want = bytes(tif._map[off:off + n]), rows * cols * 2
+        assert tiffio._lzw_decode(raw, want) == tiffio._lzw_decode_py(raw, want)
+        assert len(tiffio._lzw_decode(raw, want)) == want
+        assert np.array_equal(pg.asarray(), a)
+    # a stream that starts with a code beyond the table is rejected; a truncated one yields fewer bytes than asked
+    with pytest.raises(tiffio.TiffFormatError):
+        tiffio._lzw_decode(b"\xff\xff\xff\xff", 16)
+    assert len(tiffio._lzw_decode(raw[:len(raw) // 2], want)) < want
