@@ -191,6 +191,40 @@ def run_b200(args):
         comm.broadcast(ref_d, 0)
         comm.broadcast(mov_d, 0)
 
+    ref_sh = mov_sh = None
+    if world > 1 and args.sharded_io:
+        # the pair lives once in shared host memory; every rank page-locks just the rows it will upload
+        from microaligner_b200.engine import Engine
+        port = os.environ.get("MASTER_PORT", "0")
+        import shutil
+        import tempfile
+        shm = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > 5 * S * S else tempfile.gettempdir()
+        paths = [os.path.join(shm, f"ma_bench_{port}_{n}.u16") for n in ("ref", "mov")]
+        if rank == 0:
+            for pth, arr in zip(paths, (ref_h, mov_h)):
+                mm = np.memmap(pth, dtype=np.uint16, mode="w+", shape=(S, S))
+                mm[...] = arr
+                mm.flush()
+        dist.barrier()
+        ref_sh, mov_sh = (np.memmap(pth, dtype=np.uint16, mode="r+", shape=(S, S)) for pth in paths)
+        probe = Engine(PARAMS["tile_size"], PARAMS["overlap"], PARAMS["num_pyr_lvl"], PARAMS["num_iterations"],
+                       PARAMS["use_full_res_img"], PARAMS["use_dog"], comm=comm)
+        r0, r1 = probe.full_input_rows((S, S))
+        wb = probe.warp_band((S, S))
+        up_rows = 2 * (r1 - r0) + (min(wb[1] + PARAMS["overlap"], S) - max(wb[0] - PARAMS["overlap"], 0) if wb[1] > wb[0] else 0)
+        t_up = torch.tensor([float(up_rows) * S * 2], device=dev, dtype=torch.float64)
+        dist.all_reduce(t_up)
+        sharded_h2d = int(t_up.item())
+        for arr in (ref_sh, mov_sh):
+            rows = torch.from_numpy(arr)[r0:r1]
+            err = torch.cuda.cudart().cudaHostRegister(rows.data_ptr(), rows.numel() * rows.element_size(), 0)
+            if int(err) != 0:
+                sys.stderr.write(f"[rank {rank}] cudaHostRegister failed ({err}); uploads will be staged\n")
+        dist.barrier()
+        if rank == 0:
+            for pth in paths:
+                os.unlink(pth)       # the mappings keep the memory alive
+
     reg, wrp = OptFlowRegistrator(), Warper()
     for k, v in PARAMS.items():
         setattr(reg, k, v)
@@ -205,7 +239,19 @@ def run_b200(args):
         wrp.image, wrp.flow = mov_d, flow
         return wrp.warp()
 
+    def step_host_sharded():
+        # opt-in (--sharded-io): every rank moves only its own share over its own PCIe link -- uploads the rows of
+        # ref / mov it reads, downloads its band of the flow and of the warped image
+        reg.ref_img, reg.mov_img = ref_sh, mov_sh
+        rows, flow = reg.register_sharded()
+        wrp.image, wrp.flow = mov_sh, reg.device_flow
+        out = wrp.warp_sharded()
+        reg.device_flow = None
+        return flow, out
+
     def step_host():
+        if world > 1 and args.sharded_io:
+            return step_host_sharded()
         if world == 1:  # the drop-in numpy API
             reg.ref_img, reg.mov_img = ref_h, mov_h
             flow = reg.register()
@@ -280,6 +326,8 @@ def run_b200(args):
     img_b, flow_b = px * 2, px * 8
     if world == 1:
         h2d = 2 * img_b + img_b            # register(ref, mov) + Warper(image); the flow array is device-mirrored
+    elif args.sharded_io:
+        h2d = sharded_h2d                  # every rank: its rows of ref and mov (+ pyramid / overlap halos) and of the image to warp
     else:
         h2d = 2 * img_b                    # rank 0 uploads ref, mov; the flow stays on the devices
     d2h = flow_b + img_b                   # flow returned by register(), warped image
@@ -319,7 +367,9 @@ def run_b200(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
         "e2e": {"value": e2e_val, "unit": "Mpx/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "OptFlowRegistrator.register() + Warper.warp() on page-locked numpy arrays" if world == 1 else
-                       "rank 0: page-locked numpy in -> H2D -> NVLink broadcast -> sharded register()+warp() -> D2H of flow and image"},
+                       ("every rank: register_sharded() + warp_sharded() -- its own rows of the page-locked host pair up, its band of "
+                        "flow and image down, over its own PCIe link" if args.sharded_io else
+                        "rank 0: page-locked numpy in -> H2D -> NVLink broadcast -> sharded register()+warp() -> D2H of flow and image")},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         "contract_fma_mode": {"value": px / (ms_fast * 1e-3) / 1e6, "unit": "Mpx/s", "ms_per_step": ms_fast,
                               "note": "opt-in OptFlowRegistrator.exact_arithmetic=False; NOT the headline: flow no longer bit-identical"},
@@ -359,6 +409,9 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=4000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--use-dog", action="store_true", help="BASELINE configs[2]: same pair with the DoG prefilter enabled")
+    ap.add_argument("--sharded-io", action="store_true",
+                    help="N > 1, e2e leg only: every rank uploads its own rows and downloads its own band (register_sharded / "
+                         "warp_sharded) instead of rank 0 moving everything")
     ap.add_argument("--trace", action="store_true", help="extra untimed step with per-phase synchronised wall times (stderr)")
     args = ap.parse_args()
     if args.use_dog:

@@ -410,8 +410,9 @@ class Engine:
         return out, lay
 
     # ------------------------------------------------------------------ warp()
-    def warp(self, img: torch.Tensor, flow: torch.Tensor) -> torch.Tensor:
-        """Warper.warp (warper.py:37-76); with several ranks each warps its band and the image is gathered."""
+    def warp(self, img: torch.Tensor, flow: torch.Tensor, gather: bool = True) -> torch.Tensor:
+        """Warper.warp (warper.py:37-76); with several ranks each warps its band and the image is gathered
+        (gather=False: the result stays valid on this rank's band, Engine.warp_band(), only)."""
         L = LevelLayout(img.shape[0], img.shape[1], self.T, self.ov, self.comm)
         if self.comm.world > 1 and L.ny >= 2:
             tr = self.comm.tile_row_bands(L.ny)
@@ -419,7 +420,59 @@ class Engine:
             out = torch.empty_like(img)
             with self.phase("warp"):
                 ops.warp_tiles_rows(img, flow, self.T, self.ov, bands[self.comm.rank], out)
-            with self.phase("gather image"):
-                self.comm.gather_rows(out, bands)
+            if gather:
+                with self.phase("gather image"):
+                    self.comm.gather_rows(out, bands)
             return out
         return ops.warp_tiles(img, flow, self.T, self.ov)
+
+    # ------------------------------------------------------------------ sharded host I/O (opt-in, several ranks)
+    def warp_band(self, shape) -> Range:
+        """Rows of the warped image this rank produces in warp(): its band of tile rows, or everything when warp() is
+        not sharded."""
+        L = LevelLayout(shape[0], shape[1], self.T, self.ov, self.comm)
+        if self.comm.world > 1 and L.ny >= 2:
+            a, b = self.comm.tile_row_bands(L.ny)[self.comm.rank]
+            return _clip(a * self.T, b * self.T, L.h)
+        return (0, L.h)
+
+    def full_input_rows(self, shape) -> Range:
+        """Rows of the full-resolution ref / mov images this rank reads in register() with the band-local pyramid: the
+        support of its share of the first pyramid level, and its share of the full-resolution level if that is used."""
+        full = LevelLayout(shape[0], shape[1], self.T, self.ov, self.comm)
+        if self.comm.world == 1:
+            return (0, full.h)
+        shapes = self.level_shapes(tuple(shape))
+        need = None
+        if shapes:
+            gen = [LevelLayout(h, w, self.T, self.ov, self.comm) for h, w in shapes]
+            a, b = self.pyramid_requirements([L.input_rows(self.use_dog) for L in gen], [h for h, _ in shapes])[0]
+            if b > a:
+                need = _clip(2 * a - 2, 2 * b + 2, full.h)
+        if self.full_res:
+            r = full.input_rows(self.use_dog)
+            if r[1] > r[0]:
+                need = r if need is None else _union(need, r)
+        return need if need is not None else (0, 0)
+
+    def register_host_sharded(self, ref: np.ndarray, mov: np.ndarray, device=None):
+        """register() for host images on several ranks where every rank moves only its own share over its own PCIe link:
+        uploads the rows of ref / mov it reads (band-local pyramid), keeps the flow sharded, and downloads its band.
+        Returns (rows, flow rows [rows) as numpy, device flow valid on those rows +- overlap)."""
+        self.local_pyramid = True
+        self.gather_flow = False
+        rows_in = self.full_input_rows(ref.shape)
+        m_flow = self.register(ops.to_device_rows(ref, rows_in, device), ops.to_device_rows(mov, rows_in, device))
+        band = self.flow_layout.band if (self.flow_layout is not None and self.flow_layout.sharded) else (0, ref.shape[0])
+        return band, ops.to_host_rows(m_flow, band), m_flow
+
+    def warp_host_sharded(self, img: np.ndarray, flow: torch.Tensor):
+        """warp() for a host image and the device flow of register_host_sharded(): uploads the rows this rank's tile
+        windows read, warps its band, downloads it.  Returns (rows, warped rows [rows) as numpy)."""
+        band = self.warp_band(img.shape)
+        L = LevelLayout(img.shape[0], img.shape[1], self.T, self.ov, self.comm)
+        if L.sharded and L.ny < 2:      # a single row of tiles: warp() is replicated, so it needs the whole flow
+            self.comm.gather_rows(flow, L.bands)
+        need = _clip(band[0] - self.ov, band[1] + self.ov, img.shape[0]) if band[1] > band[0] else (0, 0)
+        out = self.warp(ops.to_device_rows(img, need, flow.device), flow, gather=False)
+        return band, ops.to_host_rows(out, band)

@@ -81,6 +81,30 @@ def to_host(t: torch.Tensor, mirror: bool = False) -> np.ndarray:
     return arr
 
 
+def to_device_rows(arr: np.ndarray, rows, device=None) -> torch.Tensor:
+    """Full-shape device tensor holding only rows [rows[0], rows[1]) of the host array (the rest stays uninitialised):
+    what one rank of a sharded run uploads over its own PCIe link."""
+    a = np.ascontiguousarray(arr)
+    if a.dtype not in (np.uint8, np.uint16, np.float32):
+        raise TypeError(f"unsupported dtype {a.dtype}; expected uint8, uint16 or float32")
+    src = torch.from_numpy(a)
+    t = torch.empty(src.shape, dtype=src.dtype, device=device or "cuda")
+    r0, r1 = int(rows[0]), int(rows[1])
+    if r1 > r0:
+        t[r0:r1].copy_(src[r0:r1], non_blocking=True)
+    return t
+
+
+def to_host_rows(t: torch.Tensor, rows) -> np.ndarray:
+    """Rows [rows[0], rows[1]) of a device tensor as a page-locked numpy array (one DMA transfer)."""
+    r0, r1 = int(rows[0]), int(rows[1])
+    host = torch.empty((max(r1 - r0, 0),) + tuple(t.shape[1:]), dtype=t.dtype, device="cpu", pin_memory=True)
+    if r1 > r0:
+        host.copy_(t[r0:r1], non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return host.numpy()
+
+
 def pinned_like(arr: np.ndarray) -> np.ndarray:
     """Copy of a numpy array in page-locked host memory (fast H2D for the drop-in numpy API)."""
     t = torch.empty(arr.shape, dtype=torch.from_numpy(arr[:0]).dtype, pin_memory=True)

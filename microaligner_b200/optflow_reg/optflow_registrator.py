@@ -118,3 +118,22 @@ class OptFlowRegistrator:
         m_flow = eng.register(ref, mov)     # the coarse-to-fine loop, sharded over the ranks of parallel.get()
         self.decisions = eng.decisions
         return ops.to_host(m_flow, mirror=self.mirror_flow) if host_result else m_flow
+
+    def register_sharded(self):
+        """Opt-in, beyond the reference, for several ranks (parallel.init) and host images: every rank uploads only the
+        rows of ref_img / mov_img it reads and downloads only its band of the flow, so the host<->device traffic is
+        spread over all ranks' PCIe links instead of funnelled through one.  ref_img / mov_img are full-shape arrays on
+        every rank (e.g. memory-mapped TIFF pages -- only this rank's rows are touched).
+        Returns (rows, flow): `flow` holds rows [rows[0], rows[1]) of the flow field; the device copy, valid on those rows
+        plus the overlap, stays in `self.device_flow` for Warper.warp_sharded()."""
+        check_img_is_provided(self._ref_img, "ref")
+        check_img_is_provided(self._mov_img, "mov")
+        check_img_dims_match(self._ref_img, self._mov_img)
+        self._init_tile_flow_calc()
+        self._init_warper()
+        eng = Engine(self.tile_size, self.overlap, self.num_pyr_lvl, self.num_iterations, self.use_full_res_img,
+                     self.use_dog, comm=parallel.get(), contract_fma=not self.exact_arithmetic,
+                     corrected=self.corrected_composition)
+        rows, flow, self.device_flow = eng.register_host_sharded(np.asarray(self._ref_img), np.asarray(self._mov_img))
+        self.decisions = eng.decisions
+        return rows, flow

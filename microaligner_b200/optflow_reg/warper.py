@@ -37,3 +37,16 @@ class Warper:
         self.flow = np.array([])
         out = Engine(self.tile_size, self.overlap, comm=parallel.get()).warp(img, flow)
         return ops.to_host(out) if host_result else out
+
+    def warp_sharded(self):
+        """Opt-in companion of OptFlowRegistrator.register_sharded() for several ranks: `image` is a full-shape host array
+        (only the rows this rank's tile windows read are uploaded), `flow` the device flow `reg.device_flow`.
+        Returns (rows, warped): rows [rows[0], rows[1]) of the warped image, computed and downloaded by this rank."""
+        if not isinstance(self.flow, torch.Tensor):
+            raise TypeError("warp_sharded() needs the device flow of register_sharded() (reg.device_flow)")
+        image, flow = np.asarray(self.image), self.flow
+        self.image = np.array([])
+        self.flow = np.array([])
+        if tuple(flow.shape) != image.shape + (2,) or flow.dtype != torch.float32:
+            raise ValueError(f"flow must be float32 of shape {image.shape + (2,)}, got {flow.dtype} {tuple(flow.shape)}")
+        return Engine(self.tile_size, self.overlap, comm=parallel.get()).warp_host_sharded(image, flow)

@@ -27,6 +27,21 @@ def to_host(t, mirror=False):
     return t.numpy().copy()
 
 
+_POISON = np.random.default_rng(99)
+
+
+def to_device_rows(arr, rows, device=None):
+    """Only rows [rows) of the host array arrive; everything else is garbage (as torch.empty would leave it)."""
+    a = np.ascontiguousarray(arr)
+    out = _POISON.integers(0, np.iinfo(a.dtype).max, a.shape, dtype=a.dtype, endpoint=True)
+    out[int(rows[0]):int(rows[1])] = a[int(rows[0]):int(rows[1])]
+    return torch.from_numpy(out)
+
+
+def to_host_rows(t, rows):
+    return t.numpy()[int(rows[0]):int(rows[1])].copy()
+
+
 def n_tiles(h, w, T):
     return (-(-h // T)) * (-(-w // T))
 

@@ -112,3 +112,45 @@ def test_sharded_engine_corner_cases(tmp_path, world, case, corrected):
         got = np.load(tmp_path / f"r{r}.npz")
         assert list(got["dec"]) == want_dec
         assert np.array_equal(got["flow"], want_flow) and np.array_equal(got["img"], want_img), f"rank {r} differs"
+
+
+def _worker_host_sharded(rank, world, port, case, tmp):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from microaligner_b200 import engine, parallel
+    from tests import mock_ops
+    parallel.init(dist.group.WORLD)
+    try:
+        engine.ops, engine.torch = mock_ops, _PoisonTorch()
+        shape, dtype, kw = CASES[case]
+        ref, mov = synth_pair(shape[0], shape[1], 3, dtype, amp=2.0, period=160.0)
+        eng = engine.Engine(kw["tile_size"], kw["overlap"], kw["num_pyr_lvl"], kw["num_iterations"], kw["use_full_res_img"],
+                            kw["use_dog"], comm=parallel.get(), log=lambda *a: None)
+        rows, flow_rows, flow_dev = eng.register_host_sharded(ref, mov)
+        wrows, img_rows = eng.warp_host_sharded(mov, flow_dev)
+        np.savez(os.path.join(tmp, f"r{rank}.npz"), rows=np.array(rows), flow=flow_rows, wrows=np.array(wrows), img=img_rows,
+                 need=np.array(eng.full_input_rows(ref.shape)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("case", list(CASES))
+def test_sharded_host_io(tmp_path, case, world):
+    """register_host_sharded / warp_host_sharded: every rank uploads only the rows of ref / mov / image it reads (the rest
+    of its device buffers is garbage) and downloads only its band; the bands of all ranks tile the single-rank result."""
+    shape, dtype, kw = CASES[case]
+    ref, mov = synth_pair(shape[0], shape[1], 3, dtype, amp=2.0, period=160.0)
+    want_flow, want_img, _ = _run(ref, mov, kw)
+    mp.spawn(_worker_host_sharded, args=(world, _free_port(), case, str(tmp_path)), nprocs=world, join=True)
+    flow_cover, img_cover = np.zeros(shape[0], int), np.zeros(shape[0], int)
+    for r in range(world):
+        got = np.load(tmp_path / f"r{r}.npz")
+        (a, b), (c, d) = got["rows"], got["wrows"]
+        assert np.array_equal(got["flow"], want_flow[a:b]), f"rank {r}: flow rows {a}:{b} differ"
+        assert np.array_equal(got["img"], want_img[c:d]), f"rank {r}: warped rows {c}:{d} differ"
+        flow_cover[a:b] += 1
+        img_cover[c:d] += 1
+        if case == "tiled levels, dog" and world == 3:       # every level sharded: a real share, not the whole image
+            assert got["need"][1] - got["need"][0] < shape[0]
+    assert (flow_cover >= 1).all() and (img_cover >= 1).all()
