@@ -198,8 +198,9 @@ def run_b200(args):
         port = os.environ.get("MASTER_PORT", "0")
         import shutil
         import tempfile
-        shm = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > 5 * S * S else tempfile.gettempdir()
-        paths = [os.path.join(shm, f"ma_bench_{port}_{n}.u16") for n in ("ref", "mov")]
+        shm = ["/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > 5 * S * S else tempfile.gettempdir()]
+        dist.broadcast_object_list(shm, src=0)      # rank 0 decides where the pair lives
+        paths = [os.path.join(shm[0], f"ma_bench_{port}_{n}.u16") for n in ("ref", "mov")]
         if rank == 0:
             for pth, arr in zip(paths, (ref_h, mov_h)):
                 mm = np.memmap(pth, dtype=np.uint16, mode="w+", shape=(S, S))
