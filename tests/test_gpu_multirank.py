@@ -90,3 +90,44 @@ def test_sharded_local_pyramid_equals_single(cuda, tmp_path, world):
         assert list(got["dec"]) == want_dec
         assert np.array_equal(got["flow"], want_flow), f"rank {r}: flow differs"
         assert np.array_equal(got["img"], want_img), f"rank {r}: warped image differs"
+
+
+def _worker_host_sharded(rank, world, port, tmp):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from microaligner_b200 import OptFlowRegistrator, Warper, parallel
+    parallel.init(dist.group.WORLD)
+    try:
+        shape, dtype, kw = LOCAL_CASE
+        ref, mov = synth_pair(shape[0], shape[1], 7, dtype)
+        reg = OptFlowRegistrator()
+        for k, v in kw.items():
+            setattr(reg, k, v)
+        reg.ref_img, reg.mov_img = ref, mov
+        with contextlib.redirect_stdout(io.StringIO()):
+            rows, flow = reg.register_sharded()
+        w = Warper()
+        w.tile_size, w.overlap = kw["tile_size"], kw["overlap"]
+        w.image, w.flow = mov, reg.device_flow
+        wrows, img = w.warp_sharded()
+        np.savez(os.path.join(tmp, f"r{rank}.npz"), rows=np.array(rows), flow=flow, wrows=np.array(wrows), img=img)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.xfail(strict=False, reason="opt-in sharded host I/O (register_sharded / warp_sharded): validated in the CPU simulation "
+                                        "(tests/test_engine_sim_cpu.py), not yet run on hardware")
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_host_io_equals_single(cuda, tmp_path, world):
+    shape, dtype, kw = LOCAL_CASE
+    ref, mov = synth_pair(shape[0], shape[1], 7, dtype)
+    want_flow, want_img, _ = _run(ref, mov, kw)
+    mp.spawn(_worker_host_sharded, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    covered = np.zeros(shape[0], int)
+    for r in range(world):
+        got = np.load(tmp_path / f"r{r}.npz")
+        (a, b), (c, d) = got["rows"], got["wrows"]
+        assert np.array_equal(got["flow"], want_flow[a:b]), f"rank {r}: flow rows differ"
+        assert np.array_equal(got["img"], want_img[c:d]), f"rank {r}: warped rows differ"
+        covered[a:b] += 1
+    assert (covered == 1).all()
