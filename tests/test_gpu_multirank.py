@@ -77,6 +77,7 @@ def test_sharded_equals_single(cuda, tmp_path, case_id, world):
         assert np.array_equal(got["img"], want_img), f"rank {r}: warped image differs"
 
 
+@pytest.mark.timeout(600)
 @pytest.mark.xfail(strict=False, reason="opt-in band-local pyramid (MA_LOCAL_PYRAMID=1): written after the round-1 GPU budget "
                                         "was spent, not yet run on hardware")
 @pytest.mark.parametrize("world", [2, 3])
@@ -115,6 +116,7 @@ def _worker_host_sharded(rank, world, port, tmp):
         dist.destroy_process_group()
 
 
+@pytest.mark.timeout(600)
 @pytest.mark.xfail(strict=False, reason="opt-in sharded host I/O (register_sharded / warp_sharded): validated in the CPU simulation "
                                         "(tests/test_engine_sim_cpu.py), not yet run on hardware")
 @pytest.mark.parametrize("world", [2, 3])
