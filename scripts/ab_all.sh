@@ -8,8 +8,8 @@ echo "== kernel variants: parity + per-kernel timing"
 timeout 120 python scripts/ab_pipeline.py > gpurun_out/ab_pipeline.log 2>&1; tail -30 gpurun_out/ab_pipeline.log | grep -v '^{'
 echo "== NMI histogram variants"
 timeout 120 python scripts/ab_nmi.py > gpurun_out/ab_nmi.log 2>&1; tail -8 gpurun_out/ab_nmi.log
-echo "== band-local pyramid on 2 / 3 gloo ranks (one GPU)"
-timeout 300 python -m pytest tests/test_gpu_multirank.py -q -k local_pyramid -rxX > gpurun_out/local_pyramid.log 2>&1; tail -5 gpurun_out/local_pyramid.log
+echo "== band-local pyramid and sharded host I/O on 2 / 3 gloo ranks (one GPU)"
+timeout 600 python -m pytest tests/test_gpu_multirank.py -q -k "local_pyramid or host_io" -rxX > gpurun_out/local_pyramid.log 2>&1; tail -5 gpurun_out/local_pyramid.log
 echo "== whole step with the candidate defaults"
 for v in "0,0,0" "2,0,0" "2,4,0" "2,4,1"; do
     MA_FB_VARIANT=$v timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > "gpurun_out/bench_variant_${v//,/_}.json" 2> "gpurun_out/bench_variant_${v//,/_}.err"
