@@ -52,13 +52,17 @@ class _PoisonTorch:
 def _run(ref, mov, kw, local_pyramid=False, corrected=False):
     from microaligner_b200 import engine, parallel
     from tests import mock_ops
+    saved = engine.ops, engine.torch
     engine.ops, engine.torch = mock_ops, _PoisonTorch()
-    eng = engine.Engine(kw["tile_size"], kw["overlap"], kw["num_pyr_lvl"], kw["num_iterations"], kw["use_full_res_img"],
-                        kw["use_dog"], comm=parallel.get(), log=lambda *a: None, corrected=corrected)
-    eng.local_pyramid = local_pyramid
-    flow = eng.register(torch.from_numpy(ref), torch.from_numpy(mov))
-    img = eng.warp(torch.from_numpy(mov), flow)
-    return flow.numpy().copy(), img.numpy().copy(), [d["better"] for d in eng.decisions]
+    try:
+        eng = engine.Engine(kw["tile_size"], kw["overlap"], kw["num_pyr_lvl"], kw["num_iterations"], kw["use_full_res_img"],
+                            kw["use_dog"], comm=parallel.get(), log=lambda *a: None, corrected=corrected)
+        eng.local_pyramid = local_pyramid
+        flow = eng.register(torch.from_numpy(ref), torch.from_numpy(mov))
+        img = eng.warp(torch.from_numpy(mov), flow)
+        return flow.numpy().copy(), img.numpy().copy(), [d["better"] for d in eng.decisions]
+    finally:
+        engine.ops, engine.torch = saved      # the single-rank run happens inside the pytest process
 
 
 def _worker(rank, world, port, case, tmp, local_pyramid, corrected=False):
