@@ -40,12 +40,9 @@ extern "C" {
 int ma_version(void);
 const char* ma_last_error(void);
 
-/* Process-wide tuning options (none changes a result).  MA_OPT_NMI_VARIANT: 0 = one pixel per thread with warp-level
- * aggregation (default), 1 = 16 pixels per thread with run-length merging before the histogram atomics. */
-#define MA_OPT_NMI_VARIANT 0
-/* MA_OPT_MINMAX_VARIANT: 0 = row loop (default), 1 = flat 4x-unrolled scan of dense, 16-byte aligned images. */
-#define MA_OPT_MINMAX_VARIANT 1
-#define MA_OPT_COUNT 2
+/* Process-wide tuning options (none changes a result); reserved for A/B measurements of kernel variants --
+ * every variant measured so far has either been promoted to the default or deleted (profiles/r02_ab_variants.log). */
+#define MA_OPT_COUNT 4
 int ma_set_option(int option, int value);
 
 /* ---- image pyramid: cv.pyrDown (optflow_reg/optflow_registrator.py:194) -------------------
@@ -117,20 +114,10 @@ int ma_farneback_tiles(const void* mov, const void* ref, size_t pitch, int dtype
  * FP32 pipe cycles in the two dominant kernels, results within ~1e-6 px of the default (inside the 0.01 / 0.1 px
  * contract per call) but no longer bit-identical to OpenCV's unfused CPU arithmetic.  Off by default. */
 #define MA_FB_CONTRACT_FMA 1u
-/* MA_FB_PIPELINED: run the window blur as persistent, warp-specialised kernels (TMA producer warp + 8 consumer
- * warps per CTA, results stored straight from registers).  Same arithmetic, bit-identical results. */
-#define MA_FB_PIPELINED 2u
-/* Experimental window-blur kernel variants, selected per pass (results are bit-identical in all of them):
- *   flags |= v << MA_FB_VARIANT_SHIFT_V   v: 0 CTA per box + shared-memory transpose (default), 1 persistent TMA ring,
- *                                            2 CTA per box + stores straight from registers, 3 = 2 with 64-row boxes
- *   flags |= h << MA_FB_VARIANT_SHIFT_H   h: 0 CTA per block + shared-memory flow stage (default), 1 persistent TMA ring,
- *                                            2 persistent ring with a rolled plane loop, 3 CTA per block + register stores,
- *                                            4 four outputs per thread (three CTAs per SM) */
-#define MA_FB_VARIANT_SHIFT_V 8
-#define MA_FB_VARIANT_SHIFT_H 12
-/*   flags |= p << MA_FB_VARIANT_SHIFT_P   p: 0 polynomial expansion staged through shared memory (default),
- *                                            1 warp-marching expansion (registers + shuffles, no barriers) */
-#define MA_FB_VARIANT_SHIFT_P 16
+/* MA_FB_FULL_WINDOWS: compute every iteration on the whole tile window.  By default each iteration is restricted to
+ * the dependency cone of the stitched tile centre (the centre grown by (iterations - 1 - it) * (win / 2) pixels):
+ * same stitched flow bit for bit, ~13 % less window-blur work at the default parameters.  For A/B measurements and tests. */
+#define MA_FB_FULL_WINDOWS 4u
 int ma_farneback_tiles_ex(const void* mov, const void* ref, size_t pitch, int dtype, int h, int w,
                           int T, int ov, int win, int iters, int tile_begin, int tile_end,
                           float* flow_out, void* workspace, size_t workspace_bytes, unsigned flags, void* stream);

@@ -84,12 +84,6 @@ for _name, (_res, _args) in PROTOTYPES.items():
     _fn.argtypes = _args
 
 
-# experimental kernel selection from the environment (results are identical in every variant)
-MA_OPT_NMI_VARIANT, MA_OPT_MINMAX_VARIANT = 0, 1
-for _env, _opt in (("MA_NMI_VARIANT", MA_OPT_NMI_VARIANT), ("MA_MINMAX_VARIANT", MA_OPT_MINMAX_VARIANT)):
-    if os.environ.get(_env, "0") not in ("", "0"):
-        lib.ma_set_option(_opt, int(os.environ[_env]))
-
 
 def check(status: int, what: str):
     if status != 0:

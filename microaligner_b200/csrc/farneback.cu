@@ -32,7 +32,7 @@
 namespace ma {
 
 constexpr int kMaxM = 96;         // TMA box rows 64 + 2*m <= 256
-constexpr int kStep = 64;         // outputs per CTA along the convolution axis (H pass; V pass: 64 or 128)
+constexpr int kStep = 64;         // outputs per CTA along the convolution axis
 constexpr int kR = 8;             // outputs per thread along the convolution axis
 
 struct FbConsts {
@@ -59,8 +59,28 @@ __device__ __forceinline__ float* slot_plane(const FbBatch& b, int slot, int whi
     return b.ws + ((size_t)slot * kSlotPlanes + which * 5 + c) * b.plane;
 }
 
+// Output window of one launch of the iteration kernels, in tile-local coordinates.  Only the centre of a tile's
+// final flow is stitched (stitcher.py:99-115), so the last iteration needs its H-pass outputs on the centre only, its
+// V-pass outputs on the centre rows x (centre +- m) columns, its M on (centre +- m)^2, hence the flow of the previous
+// iteration on (centre +- m)^2, and so on: iteration `it` of N works on the centre grown by (N-1-it)*m (H pass,
+// UpdateMatrices) resp. by that and m more columns (V pass).  Everything inside such a window is computed from
+// inputs inside the previous window, so the stitched flow is bit-identical to the untrimmed computation; what lies
+// outside is never read.  The grid covers the window of a full T x T centre from a 32-float aligned origin; tiles
+// whose centre is clipped by the image edge drop the blocks beyond their own, smaller window.
+struct FbWin {
+    int bx0, by0;   // tile-local coordinates of block (0, 0)
+    int ex, ey;     // outputs are needed on [ov - ex, ov + cw + ex) x [ov - ey, ov + ch + ey), cw x ch = clipped centre
+};
+
+__device__ __forceinline__ bool block_needed(const TileGeom& g, int tile, const FbWin& w, int x0, int xs, int y0, int ys) {
+    const int ti = tile / g.nx, tj = tile - ti * g.nx;
+    const int cw = min(g.Tw, g.w - tj * g.Tw), ch = min(g.Th, g.h - ti * g.Th);
+    return x0 < g.ov + cw + w.ex && x0 + xs > g.ov - w.ex && y0 < g.ov + ch + w.ey && y0 + ys > g.ov - w.ey;
+}
+
 // ------------------------------------------------------------------------------------------------
-// K1 + K2(first): prefilter + polynomial expansion of BOTH images of a tile, and M0 =
+// K1 + K2(first), fallback for windows narrower than 8 pixels (the marching kernel below is the default):
+// prefilter + polynomial expansion of BOTH images of a tile, and M0 =
 // UpdateMatrices(R0, R1, flow = 0), fused: with a zero flow the bilinear sample of R1 degenerates
 // to R1 at the same pixel (weights 1,0,0,0), so M0 is a pointwise function of R0 and R1 and the
 // 40 B/px re-read of a separate pass disappears.
@@ -213,6 +233,136 @@ __global__ void __launch_bounds__(256) fb_polyexp_kernel(const T* __restrict__ m
 }
 
 // ------------------------------------------------------------------------------------------------
+// K1 + K2(first), default: "marching" polynomial expansion without shared memory and without block barriers
+// (measured on B200: 0.87 ms vs 1.34 ms per 36 tiles for the staged kernel below, profiles/r02_ab_variants.log).  A warp owns a strip of 28 output columns (lanes 2..29; lanes 0, 1, 30, 31
+// carry the halo) and marches down a band of rows: per virtual row v = ya-2 .. yb+1 (actual row
+// REFLECT_101(v)) each lane loads one pixel of both images, the row prefilter takes its neighbours by
+// shuffle (sources follow REFLECT_101 at the tile edge), and the column prefilter, the vertical expansion
+// pass and the row-replication rules work on three-deep rolling registers; the horizontal pass gets T0..T2
+// of the neighbouring (replicated) columns by shuffle.  Arithmetic and its order are those of
+// fb_polyexp_kernel; tests/emu_polyexp_march.py checks the index logic against the oracle on the CPU.
+// 28/32 lanes produce output and a band re-reads 4 of its PM_BAND rows, but the ~620 instructions per pixel
+// of the staged kernel (index math, five block-wide phases per image) shrink to ~250.
+// ------------------------------------------------------------------------------------------------
+constexpr int PM_OUTW = 28;    // output columns per warp
+constexpr int PM_BAND = 96;    // output rows per warp task
+constexpr int PM_WARPS = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(PM_WARPS * 32) fb_polyexp_march_kernel(const T* __restrict__ mov, const T* __restrict__ ref,
+                                                                          size_t pitch, FbBatch b, const __grid_constant__ FbConsts cst) {
+    const TileGeom& g = b.g;
+    const int Sh = g.Sh, Sw = g.Sw;
+    const int slot = blockIdx.z;
+    const int tile = b.tile0 + slot;
+    const int ti = tile / g.nx, tj = tile % g.nx;
+    const int oy = ti * g.Th - g.ov, ox = tj * g.Tw - g.ov;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int xs = (blockIdx.x * PM_WARPS + warp) * PM_OUTW;
+    if (xs >= Sw) return;                       // warp-uniform; the kernel has no block-wide barrier
+    const int ya = blockIdx.y * PM_BAND, yb = min(ya + PM_BAND, Sh);
+    const int x = xs - 2 + lane;                // this lane's tile column
+    const bool colin = (unsigned)x < (unsigned)Sw;
+    const bool colok = colin && (unsigned)(ox + x) < (unsigned)g.w;
+    // shuffle sources: prefilter neighbours (REFLECT_101 at the tile edge) and expansion neighbours (replicate)
+    int srcL = lane, srcR = lane;
+    if (colin) {
+        srcL = min(max(reflect101(x - 1, Sw) - (xs - 2), 0), 31);
+        srcR = min(max(reflect101(x + 1, Sw) - (xs - 2), 0), 31);
+    }
+    const int tL = min(max(min(max(x - 1, 0), Sw - 1) - (xs - 2), 0), 31);
+    const int tR = min(max(min(max(x + 1, 0), Sw - 1) - (xs - 2), 0), 31);
+    const bool writer = lane >= 2 && lane < 2 + PM_OUTW && colin;
+    const T* pm = mov + (ox + x);
+    const T* pr = ref + (ox + x);
+    auto load = [&](int v, float& a, float& c) {
+        const int gy = oy + reflect101(v, Sh);
+        a = 0.0f;
+        c = 0.0f;
+        if (colok && (unsigned)gy < (unsigned)g.h) {
+            a = (float)__ldg(reinterpret_cast<const T*>(reinterpret_cast<const char*>(pm) + (size_t)gy * pitch));
+            c = (float)__ldg(reinterpret_cast<const T*>(reinterpret_cast<const char*>(pr) + (size_t)gy * pitch));
+        }
+    };
+    float th0[2] = {0, 0}, th1[2] = {0, 0}, th2[2] = {0, 0}, P0[2] = {0, 0}, P1[2] = {0, 0}, P2[2] = {0, 0};
+    float nxt[2];
+    load(ya - 2, nxt[0], nxt[1]);
+    for (int v = ya - 2; v < yb + 2; ++v) {
+        float raw[2] = {nxt[0], nxt[1]};
+        if (v + 1 < yb + 2) load(v + 1, nxt[0], nxt[1]);    // in flight during this row's arithmetic
+#pragma unroll
+        for (int im = 0; im < 2; ++im) {
+            const float l = __shfl_sync(0xffffffffu, raw[im], srcL), r = __shfl_sync(0xffffffffu, raw[im], srcR);
+            th0[im] = th1[im];
+            th1[im] = th2[im];
+            th2[im] = __fadd_rn(__fmul_rn(raw[im], 0.5f), __fmul_rn(__fadd_rn(l, r), 0.25f));
+        }
+        if (v < ya) continue;
+#pragma unroll
+        for (int im = 0; im < 2; ++im) {                     // prefiltered image at virtual row v - 1
+            P0[im] = P1[im];
+            P1[im] = P2[im];
+            P2[im] = __fadd_rn(__fmul_rn(th1[im], 0.5f), __fmul_rn(__fadd_rn(th0[im], th2[im]), 0.25f));
+        }
+        const int y = v - 2;
+        if (y < ya || y >= yb) continue;
+        float R[2][5];
+#pragma unroll
+        for (int im = 0; im < 2; ++im) {
+            const float s0 = y == 0 ? P1[im] : P0[im], sc = P1[im], s1 = y == Sh - 1 ? P1[im] : P2[im];
+            const float pp = __fadd_rn(s0, s1);
+            const float t0 = __fadd_rn(__fmul_rn(sc, cst.g0), __fmul_rn(cst.g1, pp));
+            const float t1 = __fadd_rn(0.0f, __fmul_rn(cst.xg1, __fsub_rn(s1, s0)));
+            const float t2 = __fadd_rn(0.0f, __fmul_rn(cst.xxg1, pp));
+            const float t0l = __shfl_sync(0xffffffffu, t0, tL), t0r = __shfl_sync(0xffffffffu, t0, tR);
+            const float t1l = __shfl_sync(0xffffffffu, t1, tL), t1r = __shfl_sync(0xffffffffu, t1, tR);
+            const float t2l = __shfl_sync(0xffffffffu, t2, tL), t2r = __shfl_sync(0xffffffffu, t2, tR);
+            // horizontal pass: float sums/differences, double accumulation (oracle/farneback_np.py:polyexp)
+            double b1 = (double)__fmul_rn(t0, cst.g0);
+            double b3 = (double)__fmul_rn(t1, cst.g0);
+            double b5 = (double)__fmul_rn(t2, cst.g0);
+            const double tg = (double)__fadd_rn(t0r, t0l);
+            b1 = __dadd_rn(b1, __dmul_rn(tg, (double)cst.g1));
+            const double b4 = __dmul_rn(tg, (double)cst.xxg1);
+            const double b2 = (double)__fmul_rn(__fsub_rn(t0r, t0l), cst.xg1);
+            b3 = __dadd_rn(b3, (double)__fmul_rn(__fadd_rn(t1r, t1l), cst.g1));
+            const double b6 = (double)__fmul_rn(__fsub_rn(t1r, t1l), cst.xg1);
+            b5 = __dadd_rn(b5, (double)__fmul_rn(__fadd_rn(t2r, t2l), cst.g1));
+            R[im][0] = (float)__dmul_rn(b3, cst.ig11);
+            R[im][1] = (float)__dmul_rn(b2, cst.ig11);
+            R[im][2] = (float)__dadd_rn(__dmul_rn(b1, cst.ig03), __dmul_rn(b5, cst.ig33));
+            R[im][3] = (float)__dadd_rn(__dmul_rn(b1, cst.ig03), __dmul_rn(b4, cst.ig33));
+            R[im][4] = (float)__dmul_rn(b6, cst.ig55);
+        }
+        if (!writer) continue;
+        const size_t o = (size_t)y * b.Sp + x;
+        float* __restrict__ R0p = slot_plane(b, slot, 0, 0);
+        float* __restrict__ R1p = slot_plane(b, slot, 1, 0);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            R0p[k * b.plane + o] = R[0][k];
+            R1p[k * b.plane + o] = R[1][k];
+        }
+        // UpdateMatrices with flow == 0: the sample of R1 is R1 itself where (x, y) has a right / lower neighbour
+        float r2, r3, r4, r5, r6;
+        if (x < Sw - 1 && y < Sh - 1) {
+            r2 = R[1][0];
+            r3 = R[1][1];
+            r4 = __fmul_rn(__fadd_rn(R[0][2], R[1][2]), 0.5f);
+            r5 = __fmul_rn(__fadd_rn(R[0][3], R[1][3]), 0.5f);
+            r6 = __fmul_rn(__fadd_rn(R[0][4], R[1][4]), 0.25f);
+        } else {
+            r2 = r3 = 0.0f;
+            r4 = R[0][2];
+            r5 = R[0][3];
+            r6 = __fmul_rn(R[0][4], 0.5f);
+        }
+        finish_matrices(R[0][0], R[0][1], r2, r3, r4, r5, r6, 0.0f, 0.0f, x, y, Sw, Sh, slot_plane(b, slot, 2, 0), b.plane, o);
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
 // K2: UpdateMatrices for one pixel (FarnebackUpdateMatrices, all f32, left-to-right sums)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void update_matrices_px(const float* __restrict__ R0, const float* __restrict__ R1,
@@ -269,6 +419,33 @@ constexpr int kRowU = kRowF / 2;     // packed pairs per row
 // next rows.  k2[i] = {k[i], k[i]}.
 // FUSED = false: OpenCV's separately rounded multiply and add (bit parity, the default).
 // FUSED = true : acc = fma(a[+i] + a[-i], k[i], acc) -- opt-in, 1.5x fewer FP32 pipe cycles, ~1e-6 px off.
+// one tap of conv8x2 for the 8 outputs of a thread.  The three dependent operations of an output (pair sum, product,
+// accumulate) are issued group-wise over kIlp outputs at a time, so that consecutive instructions are independent:
+// written output by output, ptxas reuses one temporary register for all chains and serialises them with 4-cycle
+// stalls (2.8 issue cycles per packed instruction instead of 2).
+#ifndef MA_CONV_ILP
+#define MA_CONV_ILP 4
+#endif
+template <bool FUSED>
+__device__ __forceinline__ void conv_step(const u64 (&wp)[kR], const u64 (&wm)[kR], int s, u64 kk, u64 nz, u64 (&acc)[kR]) {
+    constexpr int kIlp = MA_CONV_ILP;
+#pragma unroll
+    for (int j0 = 0; j0 < kR; j0 += kIlp) {
+        u64 pr[kIlp];
+#pragma unroll
+        for (int j = 0; j < kIlp; ++j) pr[j] = add2(wp[(j0 + j + s + 1) & 7], wm[(j0 + j + 63 - s) & 7]);
+        if (FUSED) {
+#pragma unroll
+            for (int j = 0; j < kIlp; ++j) acc[j0 + j] = fma2(pr[j], kk, acc[j0 + j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < kIlp; ++j) pr[j] = mul2(pr[j], kk, nz);
+#pragma unroll
+            for (int j = 0; j < kIlp; ++j) acc[j0 + j] = add2(acc[j0 + j], pr[j]);
+        }
+    }
+}
+
 template <bool FUSED>
 __device__ __forceinline__ void conv8x2(const u64* __restrict__ centre, int m, const float2* __restrict__ k2, u64 nz, u64 (&acc)[kR]) {
     u64 wp[kR], wm[kR];
@@ -291,11 +468,7 @@ __device__ __forceinline__ void conv8x2(const u64* __restrict__ centre, int m, c
             wp[s] = pp[s * kRowU];
             wm[(63 - s) & 7] = pm[-s * kRowU];
             const u64 kk = *reinterpret_cast<const u64*>(&k2[i + s]);
-#pragma unroll
-            for (int j = 0; j < kR; ++j) {
-                const u64 pr = add2(wp[(j + s + 1) & 7], wm[(j + 63 - s) & 7]);
-                acc[j] = FUSED ? fma2(pr, kk, acc[j]) : add2(acc[j], mul2(pr, kk, nz));
-            }
+            conv_step<FUSED>(wp, wm, s, kk, nz, acc);
         }
         pp += kR * kRowU;
         pm -= kR * kRowU;
@@ -306,11 +479,7 @@ __device__ __forceinline__ void conv8x2(const u64* __restrict__ centre, int m, c
             wp[s] = pp[s * kRowU];
             wm[(63 - s) & 7] = pm[-s * kRowU];
             const u64 kk = *reinterpret_cast<const u64*>(&k2[i + s]);
-#pragma unroll
-            for (int j = 0; j < kR; ++j) {
-                const u64 pr = add2(wp[(j + s + 1) & 7], wm[(j + 63 - s) & 7]);
-                acc[j] = FUSED ? fma2(pr, kk, acc[j]) : add2(acc[j], mul2(pr, kk, nz));
-            }
+            conv_step<FUSED>(wp, wm, s, kk, nz, acc);
         }
     }
 }
@@ -330,21 +499,43 @@ __device__ __forceinline__ void replicate_edges(float* buf, int rows, int v_firs
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3a: vertical pass M -> V^T.  CTA = 64 columns x OUT rows of one plane of one tile.  One TMA box
-// (64 x (OUT + 2m) floats) lands the inputs; lanes <-> column pairs; the OUT x 64 result block is
-// transposed through shared memory and written as rows of V^T (so that the horizontal pass is the
-// same kernel shape with coalesced, TMA-friendly rows).
-// grid = (ceil(Sw/64), ceil(Sh/OUT), ntiles*5), dynamic smem = (OUT + 2m) * 256 B
+// K3a: vertical pass M -> V^T.  CTA = 64 columns x 64 rows of one plane of one tile.  One TMA box (64 x (64 + 2m)
+// floats) lands the inputs; lanes <-> column pairs, warps <-> strips of 8 output rows; every thread writes its 2 x 8
+// outputs straight from registers as two 32-byte vectors of V^T (row = x, column = y), so that the horizontal pass
+// is the same kernel shape with TMA-friendly rows.  No transpose stage, no barrier after the convolution; 62
+// registers -> four CTAs per SM, whose load / convolve / store phases overlap (measured against the 128-row,
+// shared-memory-transpose version: 3.62 vs 3.79 ms per 36 tiles x 3 iterations, FMA pipe 80 % vs 76 %).
+// grid = (x blocks, y blocks, ntiles*5) over the launch window (FbWin), dynamic smem = (64 + 2m) * 256 B
 // ------------------------------------------------------------------------------------------------
-template <int OUT, bool FUSED>
+constexpr int kVOut = 64;
+
+// V pass: V^T[x][y .. y + 7] for the thread's two columns; the row pitch is a multiple of 32 floats, so a full
+// vector never leaves the row even when it runs past Sh (padding, never read back)
+__device__ __forceinline__ void store_vt_strip(const FbBatch& b, int slot, int c, int x, int y, int Sw, const u64 (&acc)[kR]) {
+    float* __restrict__ dst = slot_plane(b, slot, 3, c) + (size_t)x * b.SpT + y;
+    float2 v[kR];
+#pragma unroll
+    for (int j = 0; j < kR; ++j) v[j] = unpack2(acc[j]);
+    if (x < Sw) {
+        reinterpret_cast<float4*>(dst)[0] = make_float4(v[0].x, v[1].x, v[2].x, v[3].x);
+        reinterpret_cast<float4*>(dst)[1] = make_float4(v[4].x, v[5].x, v[6].x, v[7].x);
+    }
+    if (x + 1 < Sw) {
+        reinterpret_cast<float4*>(dst + b.SpT)[0] = make_float4(v[0].y, v[1].y, v[2].y, v[3].y);
+        reinterpret_cast<float4*>(dst + b.SpT)[1] = make_float4(v[4].y, v[5].y, v[6].y, v[7].y);
+    }
+}
+
+template <bool FUSED>
 __global__ void __launch_bounds__(256) fb_blur_v_kernel(const __grid_constant__ CUtensorMap mapM, FbBatch b,
-                                                        const __grid_constant__ FbConsts cst) {
+                                                        const __grid_constant__ FbConsts cst, FbWin win) {
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t bar;
     const int Sh = b.g.Sh, Sw = b.g.Sw, m = cst.m;
     const int slot = blockIdx.z / 5, c = blockIdx.z % 5;
-    const int x0 = blockIdx.x * kRowF, y0 = blockIdx.y * OUT;
-    const int rows = OUT + 2 * m;
+    const int x0 = win.bx0 + blockIdx.x * kRowF, y0 = win.by0 + blockIdx.y * kVOut;
+    if (!block_needed(b.g, b.tile0 + slot, win, x0, kRowF, y0, kVOut)) return;   // CTA-uniform
+    const int rows = kVOut + 2 * m;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
@@ -358,32 +549,11 @@ __global__ void __launch_bounds__(256) fb_blur_v_kernel(const __grid_constant__ 
     mbar_wait(&bar, 0);
     replicate_edges(smem, rows, y0 - m, Sh);
     const u64 nz = *reinterpret_cast<const u64*>(&cst.negzero2);
-    u64 acc[OUT / 64][kR];
-#pragma unroll
-    for (int grp = 0; grp < OUT / 64; ++grp) {
-        int o0 = grp * 64 + warp * kR;
-        if (y0 + o0 < Sh) conv8x2<FUSED>(reinterpret_cast<const u64*>(smem) + (o0 + m) * kRowU + lane, m, cst.k2, nz, acc[grp]);
-    }
-    __syncthreads();  // everyone is done reading the inputs: reuse the buffer as the transpose stage
-    constexpr int SP = OUT + 1;
-    float* stage = smem;  // [64 x][OUT + 1]
-#pragma unroll
-    for (int grp = 0; grp < OUT / 64; ++grp) {
-        int o0 = grp * 64 + warp * kR;
-        if (y0 + o0 < Sh) {
-#pragma unroll
-            for (int j = 0; j < kR; ++j) {
-                float2 v = unpack2(acc[grp][j]);
-                stage[(2 * lane) * SP + o0 + j] = v.x;
-                stage[(2 * lane + 1) * SP + o0 + j] = v.y;
-            }
-        }
-    }
-    __syncthreads();
-    float* __restrict__ dst = slot_plane(b, slot, 3, c);  // V^T plane: row = x, column = y, pitch SpT
-    for (int p = threadIdx.x; p < kRowF * OUT; p += 256) {
-        int xx = p / OUT, yy = p % OUT;
-        if (x0 + xx < Sw && y0 + yy < Sh) dst[(size_t)(x0 + xx) * b.SpT + y0 + yy] = stage[xx * SP + yy];
+    const int o0 = warp * kR;
+    if (y0 + o0 < Sh) {
+        u64 acc[kR];
+        conv8x2<FUSED>(reinterpret_cast<const u64*>(smem) + (o0 + m) * kRowU + lane, m, cst.k2, nz, acc);
+        store_vt_strip(b, slot, c, x0 + 2 * lane, y0 + o0, Sw, acc);
     }
 }
 
@@ -400,13 +570,14 @@ constexpr int kFlowPitch = 66;  // float2 per x-row of the flow stage (64 + 2: 1
 template <bool FUSED>
 __global__ void __launch_bounds__(256, 2) fb_blur_h_kernel(const __grid_constant__ CUtensorMap mapVT, FbBatch b,
                                                             const __grid_constant__ FbConsts cst, int last_iter,
-                                                            float2* __restrict__ flow_out) {
+                                                            float2* __restrict__ flow_out, FbWin win) {
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t bars[2];
     const TileGeom& g = b.g;
     const int Sh = g.Sh, Sw = g.Sw, m = cst.m;
     const int slot = blockIdx.z;
-    const int y0 = blockIdx.x * kRowF, x0 = blockIdx.y * kStep;
+    const int y0 = win.by0 + blockIdx.x * kRowF, x0 = win.bx0 + blockIdx.y * kStep;
+    if (!block_needed(g, b.tile0 + slot, win, x0, kStep, y0, kRowF)) return;   // CTA-uniform
     const int rows = kStep + 2 * m;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* buf[2] = {smem, smem + rows * kRowF};
@@ -489,21 +660,17 @@ __global__ void __launch_bounds__(256, 2) fb_blur_h_kernel(const __grid_constant
 
 // K2 (iterations > 0): M = UpdateMatrices(R0, R1, flow), one thread per tile pixel, everything coalesced
 // except the bilinear gather of R1 around (x + dx, y + dy).
-__global__ void __launch_bounds__(256) fb_update_kernel(FbBatch b) {
-    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+__global__ void __launch_bounds__(256) fb_update_kernel(FbBatch b, FbWin win) {
+    const int bx = win.bx0 + blockIdx.x * 64, by = win.by0 + blockIdx.y * 4;
     const int slot = blockIdx.z;
+    if (!block_needed(b.g, b.tile0 + slot, win, bx, 64, by, 4)) return;   // CTA-uniform
+    const int x = bx + (threadIdx.x & 63), y = by + (threadIdx.x >> 6);
     if (x >= b.g.Sw || y >= b.g.Sh) return;
     const float2 f = __ldg(reinterpret_cast<const float2*>(slot_plane(b, slot, 4, 0)) + (size_t)y * b.Sp + x);
     update_matrices_px(slot_plane(b, slot, 0, 0), slot_plane(b, slot, 1, 0), b.plane, b.Sp, b.g.Sw, b.g.Sh,
                        x, y, f.x, f.y, slot_plane(b, slot, 2, 0));
 }
 
-}  // namespace ma
-
-#include "farneback_variants.cuh"   // experimental kernel variants (MA_FB_VARIANT_SHIFT_*), none is a default
-
-namespace ma {
 
 // ------------------------------------------------------------------------------------------------
 // host side
@@ -606,20 +773,21 @@ extern "C" size_t ma_farneback_workspace_bytes(int h, int w, int T, int ov, int 
     return (size_t)n_batch * kSlotPlanes * plane_floats(g) * sizeof(float);
 }
 
+// window of one iteration along one axis: centre [ov, ov + core) grown by e, clipped to the tile window [0, S);
+// blocks start at a 32-float aligned origin
+struct Span { int origin, hi; };
+static inline Span grown_centre(int S, int core, int ov, int e, bool full) {
+    if (full) return {0, S};
+    const int lo = std::max(0, ov - e), hi = std::min(S, ov + core + e);
+    return {lo & ~31, hi};
+}
+
 extern "C" int ma_farneback_tiles_ex(const void* mov, const void* ref, size_t pitch, int dtype, int h, int w,
                                      int T, int ov, int win, int iters, int tile_begin, int tile_end,
                                      float* flow_out, void* workspace, size_t workspace_bytes, unsigned flags, void* stream) {
     const bool fused = (flags & MA_FB_CONTRACT_FMA) != 0;
-    // experimental kernel variants of the window blur (all bit-identical): bits 8..11 V pass, bits 12..15 H pass
-    //   V: 0 CTA per box + smem transpose (default), 1 persistent ring (MA_FB_PIPELINED), 2 CTA per box + register stores,
-    //      3 = 2 with 64-row boxes (more CTAs per SM)
-    //   H: 0 CTA per block + smem flow stage (default), 1 persistent ring, 2 persistent ring with rolled plane loop,
-    //      3 CTA per block + register stores, 4 four outputs per thread (3 CTAs per SM)
-    int v_var = (flags >> 8) & 15, h_var = (flags >> 12) & 15;
-    if (flags & MA_FB_PIPELINED) { if (!v_var) v_var = 1; if (!h_var) h_var = 1; }
-    const int p_var = (flags >> 16) & 15;    // polynomial expansion: 0 staged through shared memory (default), 1 marching warps
-    if (v_var > 3 || h_var > 4 || p_var > 1) return invalid("ma_farneback_tiles: unknown kernel variant");
-    const bool pipelined = v_var == 1 || v_var == 3;   // V variants 1 and 3 work on 64-output boxes
+    const bool full_windows = (flags & MA_FB_FULL_WINDOWS) != 0;   // A/B and tests: no dependency-cone trimming
+    if (flags & ~(MA_FB_CONTRACT_FMA | MA_FB_FULL_WINDOWS)) return invalid("ma_farneback_tiles: unknown flag");
     if (!mov || !ref || !flow_out || !workspace || h <= 0 || w <= 0) return invalid("ma_farneback_tiles: bad argument");
     if (dtype != MA_U8 && dtype != MA_U16) return invalid("ma_farneback_tiles: dtype must be MA_U8 or MA_U16");
     if (iters < 1) return invalid("ma_farneback_tiles: iterations must be >= 1");
@@ -643,45 +811,25 @@ extern "C" int ma_farneback_tiles_ex(const void* mov, const void* ref, size_t pi
     make_consts(win, cst);
     cudaStream_t s = (cudaStream_t)stream;
     const int m = cst.m;
-    const int vout = (m <= 49 && !pipelined) ? 128 : 64;  // V-pass rows per box: box rows vout + 2m must stay <= 256
-    const size_t pipe_smem = (size_t)kPipeStages * (kStep + 2 * m) * kRowF * sizeof(float);
-    const size_t v_smem = std::max((size_t)(vout + 2 * m) * kRowF * sizeof(float), (size_t)kRowF * (vout + 1) * sizeof(float));
+    const size_t v_smem = (size_t)(kVOut + 2 * m) * kRowF * sizeof(float);
     const size_t h_smem = std::max((size_t)2 * (kStep + 2 * m) * kRowF * sizeof(float), (size_t)kStep * kFlowPitch * sizeof(float2));
     static std::atomic<bool> attr_set[64];  // per device; setting the attributes twice is harmless
     int dev_id = 0;
     cudaGetDevice(&dev_id);
     if (dev_id < 0 || dev_id >= 64 || !attr_set[dev_id]) {
-        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 256));
-        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 256));
+        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 256));
+        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 256));
         MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_h_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 256));
-        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 256));
-        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 256));
         MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_h_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 256));
-        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeStages * 256 * 256));
-        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeStages * 256 * 256));
-        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_h_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeStages * 256 * 256));
-        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_h_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeStages * 256 * 256));
-        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_h_pipe_rolled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeStages * 256 * 256));
-        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_h_pipe_rolled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeStages * 256 * 256));
-        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_direct_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 256));
-        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_direct_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 256));
-        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_direct_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 256));
-        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_v_direct_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 256));
-        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_h_direct_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 256));
-        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_h_direct_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 256));
-        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_h4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 224 * 256));
-        MA_CUDA_CHECK(cudaFuncSetAttribute(fb_blur_h4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 224 * 256));
         if (dev_id >= 0 && dev_id < 64) attr_set[dev_id] = true;
     }
-    int n_sm = 148;
-    if (v_var == 1 || h_var == 1 || h_var == 2) MA_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev_id));
     for (int t0 = tile_begin; t0 < tile_end; t0 += cap) {
         FbBatch b;
         b.g = g; b.tile0 = t0; b.ntiles = std::min(cap, tile_end - t0);
         b.Sp = Sp; b.SpT = SpT; b.plane = plane; b.ws = (float*)workspace;
-        double tpx = (double)b.ntiles * g.Sh * g.Sw;
+        const double tpx = (double)b.ntiles * g.Sh * g.Sw;
         { KernelScope ks(K_POLYEXP, s, tpx);
-        if (p_var == 1 && g.Sh >= 8 && g.Sw >= 8) {
+        if (g.Sh >= 8 && g.Sw >= 8) {
             dim3 pg(ceil_div(ceil_div(g.Sw, PM_OUTW), PM_WARPS), ceil_div(g.Sh, PM_BAND), b.ntiles);
             if (dtype == MA_U8)
                 fb_polyexp_march_kernel<uint8_t><<<pg, PM_WARPS * 32, 0, s>>>((const uint8_t*)mov, (const uint8_t*)ref, pitch, b, cst);
@@ -695,62 +843,36 @@ extern "C" int ma_farneback_tiles_ex(const void* mov, const void* ref, size_t pi
                 fb_polyexp_kernel<uint16_t><<<pg, 256, 0, s>>>((const uint16_t*)mov, (const uint16_t*)ref, pitch, b, cst);
         } }
         // TMA descriptors over this batch's planes: M as [plane][y][x], V^T as [plane][x][y]
-        CUtensorMap mapM, mapVT, mapVT4;
+        CUtensorMap mapM, mapVT;
         uint64_t nplanes = (uint64_t)b.ntiles * kSlotPlanes;
-        if (!make_plane_map(&mapM, b.ws, g.Sw, g.Sh, nplanes, (uint64_t)Sp * 4, plane * 4, kRowF, vout + 2 * m) ||
+        if (!make_plane_map(&mapM, b.ws, g.Sw, g.Sh, nplanes, (uint64_t)Sp * 4, plane * 4, kRowF, kVOut + 2 * m) ||
             !make_plane_map(&mapVT, b.ws, g.Sh, g.Sw, nplanes, (uint64_t)SpT * 4, plane * 4, kRowF, kStep + 2 * m)) {
-            set_error("ma_farneback_tiles: cuTensorMapEncodeTiled failed");
-            return MA_ERR_CUDA;
-        }
-        if (h_var == 4 && !make_plane_map(&mapVT4, b.ws, g.Sh, g.Sw, nplanes, (uint64_t)SpT * 4, plane * 4, kRowF, kStep4 + 2 * m)) {
             set_error("ma_farneback_tiles: cuTensorMapEncodeTiled failed");
             return MA_ERR_CUDA;
         }
         for (int it = 0; it < iters; ++it) {
             const bool last = it == iters - 1;
-            { KernelScope ks(K_BLUR_V, s, tpx);
-            if (v_var == 1) {
-                const int v_items = ceil_div(g.Sw, kRowF) * ceil_div(g.Sh, kStep) * 5 * b.ntiles;
-                const int vg = std::min(v_items, 2 * n_sm);
-                if (!fused) fb_blur_v_pipe_kernel<false><<<vg, kPipeThreads, pipe_smem, s>>>(mapM, b, cst);
-                else fb_blur_v_pipe_kernel<true><<<vg, kPipeThreads, pipe_smem, s>>>(mapM, b, cst);
-            } else {
-                dim3 vg(ceil_div(g.Sw, kRowF), ceil_div(g.Sh, vout), b.ntiles * 5);
-                if (v_var == 2 || v_var == 3) {
-                    if (vout == 128 && !fused) fb_blur_v_direct_kernel<128, false><<<vg, 256, v_smem, s>>>(mapM, b, cst);
-                    else if (vout == 128) fb_blur_v_direct_kernel<128, true><<<vg, 256, v_smem, s>>>(mapM, b, cst);
-                    else if (!fused) fb_blur_v_direct_kernel<64, false><<<vg, 256, v_smem, s>>>(mapM, b, cst);
-                    else fb_blur_v_direct_kernel<64, true><<<vg, 256, v_smem, s>>>(mapM, b, cst);
-                } else {
-                    if (vout == 128 && !fused) fb_blur_v_kernel<128, false><<<vg, 256, v_smem, s>>>(mapM, b, cst);
-                    else if (vout == 128) fb_blur_v_kernel<128, true><<<vg, 256, v_smem, s>>>(mapM, b, cst);
-                    else if (!fused) fb_blur_v_kernel<64, false><<<vg, 256, v_smem, s>>>(mapM, b, cst);
-                    else fb_blur_v_kernel<64, true><<<vg, 256, v_smem, s>>>(mapM, b, cst);
-                }
-            } }
-            { KernelScope ks(K_BLUR_H, s, tpx);
-            if (h_var == 1 || h_var == 2) {
-                const int h_items = ceil_div(g.Sh, kRowF) * ceil_div(g.Sw, kStep) * b.ntiles;
-                const int hg = std::min(h_items, 2 * n_sm);
-                if (h_var == 1 && !fused) fb_blur_h_pipe_kernel<false><<<hg, kPipeThreads, pipe_smem, s>>>(mapVT, b, cst, last, (float2*)flow_out);
-                else if (h_var == 1) fb_blur_h_pipe_kernel<true><<<hg, kPipeThreads, pipe_smem, s>>>(mapVT, b, cst, last, (float2*)flow_out);
-                else if (!fused) fb_blur_h_pipe_rolled_kernel<false><<<hg, kPipeThreads, pipe_smem, s>>>(mapVT, b, cst, last, (float2*)flow_out);
-                else fb_blur_h_pipe_rolled_kernel<true><<<hg, kPipeThreads, pipe_smem, s>>>(mapVT, b, cst, last, (float2*)flow_out);
-            } else if (h_var == 4) {
-                dim3 hg(ceil_div(g.Sh, kRowF), ceil_div(g.Sw, kStep4), b.ntiles);
-                const size_t smem4 = (size_t)2 * (kStep4 + 2 * m) * kRowF * sizeof(float);
-                if (!fused) fb_blur_h4_kernel<false><<<hg, 256, smem4, s>>>(mapVT4, b, cst, last, (float2*)flow_out);
-                else fb_blur_h4_kernel<true><<<hg, 256, smem4, s>>>(mapVT4, b, cst, last, (float2*)flow_out);
-            } else {
-                dim3 hg(ceil_div(g.Sh, kRowF), ceil_div(g.Sw, kStep), b.ntiles);
-                if (h_var == 3 && !fused) fb_blur_h_direct_kernel<false><<<hg, 256, h_smem, s>>>(mapVT, b, cst, last, (float2*)flow_out);
-                else if (h_var == 3) fb_blur_h_direct_kernel<true><<<hg, 256, h_smem, s>>>(mapVT, b, cst, last, (float2*)flow_out);
-                else if (!fused) fb_blur_h_kernel<false><<<hg, 256, h_smem, s>>>(mapVT, b, cst, last, (float2*)flow_out);
-                else fb_blur_h_kernel<true><<<hg, 256, h_smem, s>>>(mapVT, b, cst, last, (float2*)flow_out);
-            } }
-            if (it < iters - 1) {
-                KernelScope ks(K_UPDATE0, s, tpx);
-                fb_update_kernel<<<dim3(ceil_div(g.Sw, 64), ceil_div(g.Sh, 4), b.ntiles), 256, 0, s>>>(b);
+            // dependency cone of the stitched centre (FbWin): this iteration's flow is needed within e of it
+            const int e = (iters - 1 - it) * m;
+            const Span hx = grown_centre(g.Sw, g.Tw, g.ov, e, full_windows), hy = grown_centre(g.Sh, g.Th, g.ov, e, full_windows);
+            const Span vx = grown_centre(g.Sw, g.Tw, g.ov, e + m, full_windows);
+            const int big = 1 << 28;   // "no trimming": every block of the grid is needed
+            const FbWin wv = {vx.origin, hy.origin, full_windows ? big : e + m, full_windows ? big : e};
+            const FbWin wh = {hx.origin, hy.origin, full_windows ? big : e, full_windows ? big : e};
+            { const int nbx = ceil_div(vx.hi - vx.origin, kRowF), nby = ceil_div(hy.hi - hy.origin, kVOut);
+            KernelScope ks(K_BLUR_V, s, (double)b.ntiles * nbx * kRowF * nby * kVOut);
+            dim3 vg(nbx, nby, b.ntiles * 5);
+            if (!fused) fb_blur_v_kernel<false><<<vg, 256, v_smem, s>>>(mapM, b, cst, wv);
+            else fb_blur_v_kernel<true><<<vg, 256, v_smem, s>>>(mapM, b, cst, wv); }
+            { const int nby = ceil_div(hy.hi - hy.origin, kRowF), nbx = ceil_div(hx.hi - hx.origin, kStep);
+            KernelScope ks(K_BLUR_H, s, (double)b.ntiles * nby * kRowF * nbx * kStep);
+            dim3 hg(nby, nbx, b.ntiles);
+            if (!fused) fb_blur_h_kernel<false><<<hg, 256, h_smem, s>>>(mapVT, b, cst, last, (float2*)flow_out, wh);
+            else fb_blur_h_kernel<true><<<hg, 256, h_smem, s>>>(mapVT, b, cst, last, (float2*)flow_out, wh); }
+            if (!last) {   // M of the next iteration: pointwise in this iteration's flow, so the same window
+                const int nbx = ceil_div(hx.hi - hx.origin, 64), nby = ceil_div(hy.hi - hy.origin, 4);
+                KernelScope ks(K_UPDATE0, s, (double)b.ntiles * nbx * 64 * nby * 4);
+                fb_update_kernel<<<dim3(nbx, nby, b.ntiles), 256, 0, s>>>(b, wh);
             }
         }
         MA_LAUNCH_CHECK("farneback kernels");

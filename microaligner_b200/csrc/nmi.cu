@@ -16,28 +16,10 @@ namespace ma {
 constexpr int kNmiSlots = 64;                       // chunks processed per group
 constexpr size_t kHistBytes = 65536 * sizeof(unsigned);
 
+// 16 pixels per thread from two 128-bit loads, equal consecutive (a, b) pairs merged in registers before the atomic
+// -- the DoG images the gate compares are smooth, so runs are long.  (Measured against one byte load per image and a
+// warp-wide match_any per pixel: 118 vs 86 Gpx/s, profiles/r02_ab_variants.log.)
 __global__ void __launch_bounds__(256) nmi_hist_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
-                                                       size_t n, size_t chunk, size_t chunk0, unsigned* __restrict__ hist) {
-    int slot = blockIdx.y;
-    size_t beg = (chunk0 + slot) * chunk;
-    size_t end = beg + chunk < n ? beg + chunk : n;
-    unsigned* H = hist + (size_t)slot * 65536;
-    size_t len = end - beg;
-    // every iteration is executed by whole warps (loop bound rounded up) so match_any sees a full mask
-    size_t iters = (len + (size_t)gridDim.x * 256 - 1) / ((size_t)gridDim.x * 256);
-    for (size_t it = 0; it < iters; ++it) {
-        size_t i = (it * gridDim.x + blockIdx.x) * 256 + threadIdx.x;
-        bool ok = i < len;
-        unsigned key = ok ? ((unsigned)__ldg(a + beg + i) << 8) | __ldg(b + beg + i) : 0xffffffffu;
-        unsigned peers = __match_any_sync(0xffffffffu, key);
-        if (ok && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&H[key], __popc(peers));
-    }
-}
-
-// Experimental variant (ma_set_option(MA_OPT_NMI_VARIANT, 1)): 16 pixels per thread from two 128-bit loads, equal
-// consecutive (a, b) pairs merged in registers before the atomic -- the DoG images the gate compares are smooth, so
-// runs are long -- instead of one byte load per image and a warp-wide match_any per pixel.  Same histogram.
-__global__ void __launch_bounds__(256) nmi_hist_rle_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
                                                            size_t n, size_t chunk, size_t chunk0, unsigned* __restrict__ hist) {
     const int slot = blockIdx.y;
     const size_t beg = (chunk0 + slot) * chunk;
@@ -180,8 +162,7 @@ extern "C" int ma_nmi_chunk_range(const uint8_t* a, const uint8_t* b, size_t n, 
         MA_CUDA_CHECK(cudaMemsetAsync(hist, 0, (size_t)g * kHistBytes, s));
         int bpc = (int)std::max<size_t>(1, std::min<size_t>((chunk + 256 * 16 - 1) / (256 * 16), (size_t)(148 * 8 + g - 1) / g));
         { KernelScope ks(K_NMI_HIST, s, (double)std::min<size_t>(n - c0 * chunk, (size_t)g * chunk));
-        if (get_option(MA_OPT_NMI_VARIANT) == 1) nmi_hist_rle_kernel<<<dim3(bpc, g), 256, 0, s>>>(a, b, n, chunk, c0, hist);
-        else nmi_hist_kernel<<<dim3(bpc, g), 256, 0, s>>>(a, b, n, chunk, c0, hist); }
+        nmi_hist_kernel<<<dim3(bpc, g), 256, 0, s>>>(a, b, n, chunk, c0, hist); }
         { KernelScope ks(K_NMI_ENTROPY, s, (double)g); nmi_entropy_kernel<<<g, 256, 0, s>>>(hist, n, chunk, c0, scores_out); }
         MA_LAUNCH_CHECK("nmi kernels");
     }

@@ -226,17 +226,8 @@ def merge_flows_tiles(f1: torch.Tensor, f2: torch.Tensor, tile_size: int, overla
 # --------------------------------------------------------------------------------- Farneback
 _FB_WS = {}
 FARNEBACK_WORKSPACE_BUDGET = 24 << 30  # bytes of HBM the tile batch may use
-# window blur as persistent, barrier-free kernels (MA_FB_PIPELINED): same results; experimental, off by default
-FB_PIPELINED = os.environ.get("MA_FB_PIPELINE", "0") not in ("", "0")
-# experimental window-blur kernel variants "v,h" (MA_FB_VARIANT_SHIFT_V / _H in the header); all bit-identical
-FB_VARIANT = tuple(int(x) for x in os.environ.get("MA_FB_VARIANT", "0,0,0").split(","))
-
-
-def _variant_bits(variant) -> int:
-    """(v, h[, p]) -> flag bits: V-pass blur << 8, H-pass blur << 12, polynomial expansion << 16."""
-    v = tuple(int(x) for x in variant) + (0, 0, 0)
-    return (v[0] << 8) | (v[1] << 12) | (v[2] << 16)
-
+# MA_FB_FULL_WINDOWS=1: no dependency-cone trimming of the iterations (A/B measurements; same results)
+FB_FULL_WINDOWS = os.environ.get("MA_FB_FULL_WINDOWS", "0") not in ("", "0")
 
 def _fb_workspace(device, nbytes: int) -> torch.Tensor:
     ws = _FB_WS.get(device)
@@ -257,11 +248,10 @@ def n_tiles(h: int, w: int, tile_size: int) -> int:
 
 def farneback_tiles(mov: torch.Tensor, ref: torch.Tensor, tile_size: int, overlap: int, win: int, iters: int,
                     tile_range=None, out: Optional[torch.Tensor] = None, contract_fma: bool = False,
-                    pipelined: Optional[bool] = None, variant: Optional[Sequence[int]] = None) -> torch.Tensor:
+                    full_windows: Optional[bool] = None) -> torch.Tensor:
     """Stitched flow of the tiled (tile_size > 0) or untiled (tile_size <= 0) Farneback.
     contract_fma=True trades bit parity for speed in the window blur (MA_FB_CONTRACT_FMA).
-    pipelined selects the persistent window-blur kernels (MA_FB_PIPELINED, same results); None = FB_PIPELINED.
-    variant = (v, h[, p]) picks experimental kernels per stage (include/microaligner_b200.h); None = FB_VARIANT."""
+    full_windows=True disables the dependency-cone trimming of the iterations (MA_FB_FULL_WINDOWS, same results)."""
     _req(mov, "moving image")
     _req(ref, "reference image")
     if mov.shape != ref.shape or mov.dtype != ref.dtype:
@@ -279,8 +269,7 @@ def farneback_tiles(mov: torch.Tensor, ref: torch.Tensor, tile_size: int, overla
     es = ref.element_size()
     check(lib.ma_farneback_tiles_ex(mov.data_ptr(), ref.data_ptr(), w * es, _code(ref), h, w, T, int(overlap), int(win),
                                     int(iters), int(t0), int(t1), out.data_ptr(), ws.data_ptr(), ws.numel(),
-                                    (1 if contract_fma else 0) | (2 if (FB_PIPELINED if pipelined is None else pipelined) else 0)
-                                    | _variant_bits(variant or FB_VARIANT),
+                                    (1 if contract_fma else 0) | (4 if (FB_FULL_WINDOWS if full_windows is None else full_windows) else 0),
                                     _stream()), "ma_farneback_tiles")
     return out
 

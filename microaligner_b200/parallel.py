@@ -125,6 +125,8 @@ class Comm:
         self.world = dist.get_world_size(group) if group is not None else 1
         self.rank = dist.get_rank(group) if group is not None else 0
         self.backend = dist.get_backend(group) if group is not None else None
+        # ranks in this module are GROUP ranks; P2POp / broadcast address peers by GLOBAL rank
+        self._global = [dist.get_global_rank(group, r) for r in range(self.world)] if group is not None else [0]
 
     # -- layout ---------------------------------------------------------------------------------
     def tile_row_bands(self, ny: int) -> List[Range]:
@@ -150,10 +152,10 @@ class Comm:
             view = tw[a:b]
             if src == self.rank:
                 buf = view.cpu() if stage_cpu else view
-                ops.append(dist.P2POp(dist.isend, buf, dst, group=self.group))
+                ops.append(dist.P2POp(dist.isend, buf, self._global[dst], group=self.group))
             else:
                 buf = torch.empty(view.shape, dtype=view.dtype, device="cpu") if stage_cpu else view
-                ops.append(dist.P2POp(dist.irecv, buf, src, group=self.group))
+                ops.append(dist.P2POp(dist.irecv, buf, self._global[src], group=self.group))
                 if stage_cpu:
                     recvs.append((view, buf))
         for req in dist.batch_isend_irecv(ops):
@@ -177,11 +179,11 @@ class Comm:
             view = tw[y0:y1, x0 * scale:x1 * scale]
             if src == self.rank:
                 buf = view.contiguous()
-                ops.append(dist.P2POp(dist.isend, buf.cpu() if cpu else buf, dst, group=self.group))
+                ops.append(dist.P2POp(dist.isend, buf.cpu() if cpu else buf, self._global[dst], group=self.group))
             else:
                 direct = view.is_contiguous() and not cpu
                 buf = view if direct else torch.empty(view.shape, dtype=view.dtype, device="cpu" if cpu else view.device)
-                ops.append(dist.P2POp(dist.irecv, buf, src, group=self.group))
+                ops.append(dist.P2POp(dist.irecv, buf, self._global[src], group=self.group))
                 if not direct:
                     recvs.append((view, buf))
         for req in dist.batch_isend_irecv(ops):
@@ -222,7 +224,7 @@ class Comm:
 
     def broadcast(self, t: torch.Tensor, src: int = 0):
         if self.world > 1:
-            dist.broadcast(self._wire(t), src=src, group=self.group)
+            dist.broadcast(self._wire(t), src=self._global[src], group=self.group)
         return t
 
 

@@ -142,7 +142,9 @@ class TiffPage:
         """The page as a (height, width) array in native byte order; a zero-copy memmap view for uncompressed pages
         whose strips are contiguous in the file."""
         if self.is_contiguous:
-            a = np.ndarray(self.shape, self.dtype, buffer=self._tif._map, offset=self.offsets[0])
+            # np.memmap owns its own mapping of the file, so the array stays valid after TiffFile.close() -- the
+            # reference returns the page after its with-block (shared_modules/utils.py:69-72)
+            a = np.memmap(self._tif.path, dtype=self.dtype, mode="r", offset=self.offsets[0], shape=self.shape)
             return a if a.dtype.isnative else a.astype(a.dtype.newbyteorder("="))
         return self.read_into(np.empty(self.shape, self.dtype.newbyteorder("=")))
 

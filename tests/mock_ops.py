@@ -139,8 +139,7 @@ def compose_flows_rows(f1, f2, rows, out):
 
 
 # ------------------------------------------------------------------ Farneback
-def farneback_tiles(mov, ref, tile_size, overlap, win, iters, tile_range=None, out=None, contract_fma=False, pipelined=None,
-                    variant=None):
+def farneback_tiles(mov, ref, tile_size, overlap, win, iters, tile_range=None, out=None, contract_fma=False, full_windows=None):
     m, r = _np(mov), _np(ref)
     h, w = r.shape
     T, ov = int(tile_size), int(overlap)

@@ -78,8 +78,6 @@ def test_sharded_equals_single(cuda, tmp_path, case_id, world):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.xfail(strict=False, reason="opt-in band-local pyramid (MA_LOCAL_PYRAMID=1): written after the round-1 GPU budget "
-                                        "was spent, not yet run on hardware")
 @pytest.mark.parametrize("world", [2, 3])
 def test_sharded_local_pyramid_equals_single(cuda, tmp_path, world):
     shape, dtype, kw = LOCAL_CASE
@@ -117,8 +115,6 @@ def _worker_host_sharded(rank, world, port, tmp):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.xfail(strict=False, reason="opt-in sharded host I/O (register_sharded / warp_sharded): validated in the CPU simulation "
-                                        "(tests/test_engine_sim_cpu.py), not yet run on hardware")
 @pytest.mark.parametrize("world", [2, 3])
 def test_sharded_host_io_equals_single(cuda, tmp_path, world):
     shape, dtype, kw = LOCAL_CASE

@@ -208,3 +208,20 @@ def test_native_lzw_decoder_matches_python_and_rejects_garbage(tmp_path):
     with pytest.raises(tiffio.TiffFormatError):
         tiffio._lzw_decode(b"\xff\xff\xff\xff", 16)
     assert len(tiffio._lzw_decode(raw[:len(raw) // 2], want)) < want
+
+
+def test_page_array_outlives_the_file(tmp_path):
+    """The reference returns the page after its with-block (shared_modules/utils.py:69-72): the array must stay valid
+    once the TiffFile is closed (a view over the file's own mmap dangled)."""
+    a = np.stack(pages(3)).reshape(1, 1, 3, 50, 70)
+    p = tmp_path / "stack.tif"
+    tiffio.imwrite(p, a)
+    with tiffio.TiffFile(p) as tif:
+        first = tif.series[0].pages[0].asarray()
+        whole = tif.asarray()
+    assert np.array_equal(first, a[0, 0, 0]) and np.array_equal(whole.reshape(3, 50, 70), a[0, 0])
+    single = tmp_path / "single.tif"
+    tiffio.imwrite(single, a[0, 0, 1])
+    with tiffio.TiffFile(single) as tif:
+        one = tif.asarray()
+    assert np.array_equal(one, a[0, 0, 1]) and int(one.sum()) == int(a[0, 0, 1].astype(np.int64).sum())
