@@ -146,7 +146,8 @@ int ma_dog_quantize_rows(const float* diff, int diff_row0, int h, int w, const f
 /* ---- mi_tiled (shared_modules/similarity_scoring.py:27-50): normalized mutual information
  * (sklearn, arithmetic mean, natural log) of two u8 label images over consecutive chunks of
  * `chunk` row-major elements of the dense n-element arrays; scores_out[c] (double, device) gets
- * one NMI per chunk c < ceil(n/chunk).  workspace: ma_nmi_workspace_bytes(n, chunk). */
+ * one NMI per chunk c < ceil(n/chunk).  The joint histograms live in distributed shared memory (one four-CTA cluster
+ * per chunk): ma_nmi_workspace_bytes returns 0 and `workspace` may be NULL (both kept for ABI stability). */
 size_t ma_nmi_workspace_bytes(size_t n, size_t chunk);
 int ma_nmi_chunks(const uint8_t* a, const uint8_t* b, size_t n, size_t chunk,
                   double* scores_out, void* workspace, void* stream);

@@ -24,6 +24,7 @@ namespace ma {
 
 struct DogTaps {
     float k5[41], k9[41];
+    float2 k59[41];          // {k5[j], k9[j]}: both sigmas of the row pass in one packed f32x2 FMA
     float2 c5[21], c9[21];   // k[20 + j] duplicated {k, k}: taps of the symmetric column pass (packed f32x2)
     float2 negzero2;         // {-0.f, -0.f}, see packed.cuh:mul2
 };
@@ -39,7 +40,10 @@ static void make_dog_taps(DogTaps& t) {
             sum += k[i];
         }
         sum = 1. / sum;
-        for (int i = 0; i < 41; ++i) (which ? t.k9 : t.k5)[i] = (float)(k[i] * sum);
+        for (int i = 0; i < 41; ++i) {
+            (which ? t.k9 : t.k5)[i] = (float)(k[i] * sum);
+            (which ? t.k59[i].y : t.k59[i].x) = (float)(k[i] * sum);
+        }
         for (int j = 0; j <= 20; ++j) {
             float v = (which ? t.k9 : t.k5)[20 + j];
             (which ? t.c9 : t.c5)[j] = make_float2(v, v);
@@ -220,13 +224,25 @@ __global__ void __launch_bounds__(DOG_HT) dog_row_kernel(const T* __restrict__ s
         }
         float s5[4] = {0.f, 0.f, 0.f, 0.f}, s9[4] = {0.f, 0.f, 0.f, 0.f};
         if (fused) {
+            // both sigmas of an output share one packed f32x2 accumulator {s5, s9}: input i, broadcast to both halves,
+            // meets tap j = i - o of output o -- the same 41 FMAs per sum in the same order, in half the issue slots
+            // (the scalar version was issue-bound at 89 %, ncu r01)
+            u64 acc[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
-            for (int j = 0; j < 41; ++j)
+            for (int i = 0; i < 44; ++i) {
+                const u64 p = pack2(in[i], in[i]);
 #pragma unroll
                 for (int o = 0; o < 4; ++o) {
-                    s5[o] = __fmaf_rn(in[o + j], taps.k5[j], s5[o]);
-                    s9[o] = __fmaf_rn(in[o + j], taps.k9[j], s9[o]);
+                    const int j = i - o;
+                    if (j >= 0 && j < 41) acc[o] = fma2(p, *reinterpret_cast<const u64*>(&taps.k59[j]), acc[o]);
                 }
+            }
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                const float2 v = unpack2(acc[o]);
+                s5[o] = v.x;
+                s9[o] = v.y;
+            }
         } else {  // scalar tail: multiply and add rounded separately
 #pragma unroll
             for (int j = 0; j < 41; ++j)

@@ -247,6 +247,7 @@ __global__ void __launch_bounds__(256) fb_polyexp_kernel(const T* __restrict__ m
 constexpr int PM_OUTW = 28;    // output columns per warp
 constexpr int PM_BAND = 96;    // output rows per warp task
 constexpr int PM_WARPS = 8;
+constexpr int kPmDepth = 4;   // rows of both images in flight per lane
 
 template <typename T>
 __global__ void __launch_bounds__(PM_WARPS * 32) fb_polyexp_march_kernel(const T* __restrict__ mov, const T* __restrict__ ref,
@@ -285,11 +286,20 @@ __global__ void __launch_bounds__(PM_WARPS * 32) fb_polyexp_march_kernel(const T
         }
     };
     float th0[2] = {0, 0}, th1[2] = {0, 0}, th2[2] = {0, 0}, P0[2] = {0, 0}, P1[2] = {0, 0}, P2[2] = {0, 0};
-    float nxt[2];
-    load(ya - 2, nxt[0], nxt[1]);
-    for (int v = ya - 2; v < yb + 2; ++v) {
-        float raw[2] = {nxt[0], nxt[1]};
-        if (v + 1 < yb + 2) load(v + 1, nxt[0], nxt[1]);    // in flight during this row's arithmetic
+    // kPmDepth - 1 rows are in flight behind the row being processed (one row was not enough to cover the DRAM latency:
+    // ncu showed the kernel waiting on its loads at 38 % of DRAM peak); the queue rotates through static indices
+    float q[kPmDepth][2];
+    const int vend = yb + 2;
+#pragma unroll
+    for (int k = 0; k < kPmDepth - 1; ++k)
+        if (ya - 2 + k < vend) load(ya - 2 + k, q[k][0], q[k][1]);
+    for (int vb = ya - 2; vb < vend; vb += kPmDepth)
+#pragma unroll
+    for (int k = 0; k < kPmDepth; ++k) {
+        const int v = vb + k;
+        if (v >= vend) break;
+        if (v + kPmDepth - 1 < vend) load(v + kPmDepth - 1, q[(k + kPmDepth - 1) % kPmDepth][0], q[(k + kPmDepth - 1) % kPmDepth][1]);
+        float raw[2] = {q[k][0], q[k][1]};
 #pragma unroll
         for (int im = 0; im < 2; ++im) {
             const float l = __shfl_sync(0xffffffffu, raw[im], srcL), r = __shfl_sync(0xffffffffu, raw[im], srcR);
@@ -618,13 +628,13 @@ __global__ void __launch_bounds__(256, 2) fb_blur_h_kernel(const __grid_constant
             float4 o;
             {
                 double g11 = G11.x, g12 = G12.x, g22 = G22.x, h1 = H1.x, h2 = H2.x;
-                double idet = __ddiv_rn(1.0, __dadd_rn(__dsub_rn(__dmul_rn(g11, g22), __dmul_rn(g12, g12)), 1e-3));
+                double idet = __drcp_rn(__dadd_rn(__dsub_rn(__dmul_rn(g11, g22), __dmul_rn(g12, g12)), 1e-3));
                 o.x = (float)__dmul_rn(__dsub_rn(__dmul_rn(g11, h2), __dmul_rn(g12, h1)), idet);
                 o.y = (float)__dmul_rn(__dsub_rn(__dmul_rn(g22, h1), __dmul_rn(g12, h2)), idet);
             }
             {
                 double g11 = G11.y, g12 = G12.y, g22 = G22.y, h1 = H1.y, h2 = H2.y;
-                double idet = __ddiv_rn(1.0, __dadd_rn(__dsub_rn(__dmul_rn(g11, g22), __dmul_rn(g12, g12)), 1e-3));
+                double idet = __drcp_rn(__dadd_rn(__dsub_rn(__dmul_rn(g11, g22), __dmul_rn(g12, g12)), 1e-3));
                 o.z = (float)__dmul_rn(__dsub_rn(__dmul_rn(g11, h2), __dmul_rn(g12, h1)), idet);
                 o.w = (float)__dmul_rn(__dsub_rn(__dmul_rn(g22, h1), __dmul_rn(g12, h2)), idet);
             }

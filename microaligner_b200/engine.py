@@ -111,10 +111,15 @@ class Engine:
         self.decisions: List[dict] = []
         self.force_decisions = None  # test hook (list of bools per level), mirrors oracle.reference_flow.register
         self.gather_flow = True      # False: with several ranks the returned flow is valid on this rank's band only
-        # opt-in (MA_LOCAL_PYRAMID=1), several ranks only: every rank reduces just the rows of each pyramid level it
-        # will read (LevelLayout.input_rows) from its replicated copy of the input, instead of computing a slice of
-        # every level and gathering the levels over NVLink.  Rows outside that range stay uninitialised.
-        self.local_pyramid = os.environ.get("MA_LOCAL_PYRAMID", "0") not in ("", "0")
+        # several ranks only: every rank reduces just the rows of each pyramid level it will read
+        # (LevelLayout.input_rows) from its copy of the input -- of which only Engine.full_input_rows() need to be valid
+        # -- instead of computing a slice of every level and gathering the levels over NVLink.  Rows outside that range
+        # stay uninitialised.  MA_LOCAL_PYRAMID=0 selects the gathering variant (A/B measurements).
+        self.local_pyramid = os.environ.get("MA_LOCAL_PYRAMID", "1") not in ("", "0")
+        # rows of the final flow are handed to a host sink as soon as they are final; on one GPU the last level runs its
+        # Farneback tile row by tile row and merges / downloads speculatively behind it (see register())
+        self.stream_groups = True
+        self.group_tiles = 40        # tiles per Farneback launch of that streamed last level (enough CTAs to fill 148 SMs)
         self.flow_layout = None
 
     def log(self, *a):
@@ -254,7 +259,9 @@ class Engine:
         return ops.pyr_up_flow_rows(flow, (Ld.h, Ld.w), scale, Ld.band, out)
 
     # ------------------------------------------------------------------ register()
-    def register(self, ref: torch.Tensor, mov: torch.Tensor) -> torch.Tensor:
+    def register(self, ref: torch.Tensor, mov: torch.Tensor, sink=None, ready=(None, None)) -> torch.Tensor:
+        """The coarse-to-fine loop.  `sink` (ops.HostSink) receives this rank's rows of the final flow while the device
+        keeps working; `ready` = events to wait for before ref / mov are read (asynchronous uploads)."""
         comm, T, ov = self.comm, self.T, self.ov
         full = LevelLayout(ref.shape[0], ref.shape[1], T, ov, comm)
         with self.phase("pyramid"):
@@ -264,10 +271,15 @@ class Engine:
                 req = self.pyramid_requirements([L.input_rows(self.use_dog) for L in gen], [h for h, _ in shapes])
                 if self.num_pyr_lvl < 0 or (not shapes and not self.full_res):
                     self.pyramid(ref)                                               # raises the reference's ValueErrors
-                ref_pyr, mov_pyr = self.pyramid_local(ref, shapes, req), self.pyramid_local(mov, shapes, req)
+                ops.wait_upload(ready[0])
+                ref_pyr = self.pyramid_local(ref, shapes, req)
+                ops.wait_upload(ready[1])
+                mov_pyr = self.pyramid_local(mov, shapes, req)
                 factors = [2 ** (k + 1) for k in range(len(shapes))][::-1] + ([1] if self.full_res else [])
             else:
+                ops.wait_upload(ready[0])
                 ref_pyr, factors = self.pyramid(ref)
+                ops.wait_upload(ready[1])                # the pyramid of ref runs while mov is still arriving
                 mov_pyr, _ = self.pyramid(mov)
         layouts = [LevelLayout(p.shape[0], p.shape[1], T, ov, comm) for p in ref_pyr]
         num_lvl = len(factors)
@@ -317,8 +329,28 @@ class Engine:
                 fb_mov = dogs[2] if self.use_dog else mov_l
                 del dogs, items
             this_flow = torch.empty((L.h, L.w, 2), dtype=torch.float32, device=ref.device)
+            # Speculative tail of the LAST level on one GPU: if the gate accepts this level -- it nearly always does --
+            # the result is merge(m_flow, this_flow), which is per tile.  So the Farneback tiles run one group of tile
+            # rows at a time, every tile row whose window is complete is merged right behind it, and its rows start
+            # their way to the host while the next group is computed.  Should the gate reject the level, the rows are
+            # simply sent again from the flow that is returned instead.
+            speculate = (sink is not None and self.stream_groups and L.tiled and not L.sharded and comm.world == 1
+                         and lvl == num_lvl - 1 and lvl > 0 and self.full_res and not self.corrected)
+            merged, merged_hi = None, 0
             with self.phase("farneback" if L.tiled else "farneback(untiled level)"):
-                if L.tiled:
+                if speculate:
+                    merged = torch.empty_like(this_flow)
+                    step = max(1, -(-self.group_tiles // L.nx))     # tile rows per group
+                    for i0 in range(0, L.ny, step):
+                        i1 = min(i0 + step, L.ny)
+                        ops.farneback_tiles(fb_mov, fb_ref, T, ov, self.win, self.iters, (i0 * L.nx, i1 * L.nx), out=this_flow,
+                                            contract_fma=self.contract_fma)
+                        ready_hi = i1 if i1 == L.ny else i1 - 1     # tile row i reads rows up to (i + 1) T + ov
+                        if ready_hi > merged_hi:
+                            ops.merge_flows_tile_rows(m_flow, this_flow, T, ov, (merged_hi, ready_hi), merged)
+                            sink.push(merged, _clip(merged_hi * T, ready_hi * T, L.h))
+                            merged_hi = ready_hi
+                elif L.tiled:
                     ops.farneback_tiles(fb_mov, fb_ref, T, ov, self.win, self.iters, L.fb_tiles[L.rank], out=this_flow,
                                         contract_fma=self.contract_fma)
                 else:
@@ -357,7 +389,10 @@ class Engine:
                     else:
                         m_flow, m_layout = self._upscale_to_full(this_flow, L, full, factor)
                 elif lvl == num_lvl - 1:
-                    merged = self._merge(m_flow, this_flow, L)
+                    if merged is None:
+                        merged = self._merge(m_flow, this_flow, L)
+                    else:
+                        sink = None                      # every row of the result is already on its way to the host
                     m_flow, m_layout = merged, L
                     if not self.full_res:
                         m_flow, m_layout = self._upscale_to_full(merged, L, full, factor)
@@ -382,6 +417,8 @@ class Engine:
             # no pyramid level at all: the reference fails on its unbound local (optflow_registrator.py:173)
             raise UnboundLocalError("cannot access local variable 'm_flow' where it is not associated with a value")
         self.flow_layout = m_layout
+        if sink is not None:       # not (or wrongly) speculated: this rank's rows of the result go to the host now
+            sink.push(m_flow, self.result_rows(m_layout, m_flow.shape[0]))
         if self.gather_flow and m_layout is not None and m_layout.sharded:
             with self.phase("gather flow"):
                 comm.gather_rows(m_flow, m_layout.bands)
@@ -426,7 +463,14 @@ class Engine:
             return out
         return ops.warp_tiles(img, flow, self.T, self.ov)
 
-    # ------------------------------------------------------------------ sharded host I/O (opt-in, several ranks)
+    # ------------------------------------------------------------------ host images in, host arrays out
+    def result_rows(self, layout: Optional[LevelLayout], h: int) -> Range:
+        """Rows of a result this rank delivers to the host: its band where the result is sharded, else an even share of
+        the replicated result (every rank holds all of it; the download is still spread over all PCIe links)."""
+        if layout is not None and layout.sharded:
+            return layout.band
+        return parallel.split_even(h, self.comm.world)[self.comm.rank]
+
     def warp_band(self, shape) -> Range:
         """Rows of the warped image this rank produces in warp(): its band of tile rows, or everything when warp() is
         not sharded."""
@@ -440,7 +484,7 @@ class Engine:
         """Rows of the full-resolution ref / mov images this rank reads in register() with the band-local pyramid: the
         support of its share of the first pyramid level, and its share of the full-resolution level if that is used."""
         full = LevelLayout(shape[0], shape[1], self.T, self.ov, self.comm)
-        if self.comm.world == 1:
+        if self.comm.world == 1 or not self.local_pyramid:
             return (0, full.h)
         shapes = self.level_shapes(tuple(shape))
         need = None
@@ -455,24 +499,58 @@ class Engine:
                 need = r if need is None else _union(need, r)
         return need if need is not None else (0, 0)
 
-    def register_host_sharded(self, ref: np.ndarray, mov: np.ndarray, device=None):
-        """register() for host images on several ranks where every rank moves only its own share over its own PCIe link:
-        uploads the rows of ref / mov it reads (band-local pyramid), keeps the flow sharded, and downloads its band.
-        Returns (rows, flow rows [rows) as numpy, device flow valid on those rows +- overlap)."""
-        self.local_pyramid = True
+    def register_host(self, ref: np.ndarray, mov: np.ndarray, device=None):
+        """register() for HOST images, the path behind the drop-in numpy API on 1..N GPUs.
+
+        Every rank moves only its own share over its own PCIe link: it uploads the rows of ref / mov it reads
+        (full_input_rows; everything on one GPU) on a copy stream -- the pyramid of ref is built while mov is still
+        arriving -- keeps the flow sharded on the devices, and its rows of the result travel to the host on a side
+        stream as soon as they are final (speculatively behind the last level's Farneback on one GPU).  The result is one
+        full (H, W, 2) array: page-locked memory on one GPU, node-shared memory mapped by all ranks otherwise (complete
+        on every rank when the call returns).  Returns (flow array, device flow valid on this rank's rows +- overlap)."""
+        comm = self.comm
         self.gather_flow = False
         rows_in = self.full_input_rows(ref.shape)
-        m_flow = self.register(ops.to_device_rows(ref, rows_in, device), ops.to_device_rows(mov, rows_in, device))
-        band = self.flow_layout.band if (self.flow_layout is not None and self.flow_layout.sharded) else (0, ref.shape[0])
-        return band, ops.to_host_rows(m_flow, band), m_flow
+        ref_d, ev_r = ops.upload_rows(ref, rows_in, device)
+        mov_d, ev_m = ops.upload_rows(mov, rows_in, device)
+        shape = tuple(ref.shape) + (2,)
+        if comm.world == 1:
+            out = ops.host_result(shape, np.float32)
+        else:      # node-shared block, recycled from call to call: this rank's rows of it stay page-locked
+            out = comm.shared_host_empty(shape, np.float32)
+            ops.pin_rows(out, self.result_rows(LevelLayout(shape[0], shape[1], self.T, self.ov, comm), shape[0]))
+        sink = ops.HostSink(out)
+        m_flow = self.register(ref_d, mov_d, sink=sink, ready=(ev_r, ev_m))
+        sink.wait()
+        comm.barrier()            # node-shared result: complete once every rank's rows have landed
+        return out, m_flow
 
-    def warp_host_sharded(self, img: np.ndarray, flow: torch.Tensor):
-        """warp() for a host image and the device flow of register_host_sharded(): uploads the rows this rank's tile
-        windows read, warps its band, downloads it.  Returns (rows, warped rows [rows) as numpy)."""
+    def warp_host(self, img: np.ndarray, flow: torch.Tensor):
+        """warp() for a host image and a device flow valid on this rank's band +- overlap (register_host's, or an
+        uploaded one): uploads the rows this rank's tile windows read, warps its band, downloads it into the shared
+        result.  Several ranks only -- one GPU streams tile rows through ops.warp_tiles_host_streamed."""
+        comm = self.comm
         band = self.warp_band(img.shape)
-        L = LevelLayout(img.shape[0], img.shape[1], self.T, self.ov, self.comm)
+        L = LevelLayout(img.shape[0], img.shape[1], self.T, self.ov, comm)
         if L.sharded and L.ny < 2:      # a single row of tiles: warp() is replicated, so it needs the whole flow
-            self.comm.gather_rows(flow, L.bands)
+            comm.gather_rows(flow, L.bands)
         need = _clip(band[0] - self.ov, band[1] + self.ov, img.shape[0]) if band[1] > band[0] else (0, 0)
-        out = self.warp(ops.to_device_rows(img, need, flow.device), flow, gather=False)
-        return band, ops.to_host_rows(out, band)
+        img_d, ev = ops.upload_rows(img, need, flow.device)
+        ops.wait_upload(ev)
+        out_d = self.warp(img_d, flow, gather=False)
+        rows = band if (comm.world > 1 and L.ny >= 2) else self.result_rows(None, img.shape[0])
+        if comm.world > 1:
+            out = comm.shared_host_empty(img.shape, img.dtype)
+            ops.pin_rows(out, rows)
+        else:
+            out = ops.host_result(img.shape, img.dtype)
+        sink = ops.HostSink(out)
+        sink.push(out_d, rows)
+        sink.wait()
+        comm.barrier()
+        return out
+
+    def flow_rows_needed(self, shape) -> Range:
+        """Rows of a host flow this rank has to upload for warp_host(): its warp band +- overlap."""
+        band = self.warp_band(shape)
+        return _clip(band[0] - self.ov, band[1] + self.ov, shape[0]) if band[1] > band[0] else (0, 0)

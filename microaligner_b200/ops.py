@@ -47,15 +47,23 @@ def _bytes(n: int, device) -> torch.Tensor:
 _MIRRORS = {}   # id(host array) -> (weakref to the array, device tensor it mirrors)
 
 
+def mirrored(arr):
+    """The device tensor a read-only result array mirrors (see mirror()), or None."""
+    m = _MIRRORS.get(id(arr))
+    if m is not None and m[0]() is arr and not arr.flags.writeable:
+        return m[1]
+    return None
+
+
 def to_device(arr, device=None) -> torch.Tensor:
     """numpy (uint8/uint16/float32) or torch tensor -> contiguous CUDA tensor.  A read-only array handed out
     by to_host(mirror=True) is recognised by identity and mapped back to its device copy without a transfer."""
     if isinstance(arr, torch.Tensor):
         t = arr if arr.is_cuda else arr.to(device or "cuda")
         return t.contiguous()
-    m = _MIRRORS.get(id(arr))
-    if m is not None and m[0]() is arr and not arr.flags.writeable:
-        return m[1]
+    m = mirrored(arr)
+    if m is not None:
+        return m
     a = np.ascontiguousarray(arr)
     if a.dtype not in (np.uint8, np.uint16, np.float32):
         raise TypeError(f"unsupported dtype {a.dtype}; expected uint8, uint16 or float32")
@@ -103,6 +111,145 @@ def to_host_rows(t: torch.Tensor, rows) -> np.ndarray:
         host.copy_(t[r0:r1], non_blocking=True)
     torch.cuda.current_stream().synchronize()
     return host.numpy()
+
+
+# ---- caller-owned host memory: page-locking on reuse, asynchronous row uploads, streamed downloads -------------------
+_SEEN = {}       # (address, nbytes) -> times a pageable host range was uploaded
+_REGISTERED = {}  # (address, nbytes) -> True for ranges page-locked with cudaHostRegister
+PIN_MIN_BYTES = 32 << 20
+
+
+def _unregister(key):
+    if _REGISTERED.pop(key, None):
+        try:
+            torch.cuda.cudart().cudaHostUnregister(key[0])
+        except Exception:  # interpreter shutdown
+            pass
+
+
+def _register(arr: np.ndarray, view: torch.Tensor) -> bool:
+    key = (view.data_ptr(), view.numel() * view.element_size())
+    if key in _REGISTERED:
+        return True
+    if int(torch.cuda.cudart().cudaHostRegister(key[0], key[1], 0)) != 0:
+        torch.cuda.cudart().cudaGetLastError()
+        _SEEN[key] = -(1 << 30)        # do not try again
+        return False
+    _REGISTERED[key] = True
+    owner = arr
+    while isinstance(getattr(owner, "base", None), np.ndarray):
+        owner = owner.base
+    try:
+        weakref.finalize(owner, _unregister, key)
+    except TypeError:
+        pass
+    return True
+
+
+def pin_on_reuse(arr: np.ndarray, view: torch.Tensor) -> bool:
+    """Page-lock the memory of `view` (a CPU tensor over rows of the caller's array `arr`) with cudaHostRegister the
+    SECOND time the same range is uploaded: a one-off upload of pageable memory is cheaper staged (registration costs
+    about as much as one staged copy), a repeated one -- the same reference image against many moving images, bench
+    loops -- then runs at DMA line rate.  The registration is dropped when `arr` is garbage collected."""
+    if view.numel() == 0 or view.is_pinned():
+        return True
+    nbytes = view.numel() * view.element_size()
+    key = (view.data_ptr(), nbytes)
+    if nbytes < PIN_MIN_BYTES:
+        return False
+    n = _SEEN.get(key, 0) + 1
+    _SEEN[key] = n
+    return _register(arr, view) if n >= 2 else False
+
+
+def pin_rows(arr: np.ndarray, rows) -> bool:
+    """Page-lock rows [rows[0], rows[1]) of a host array now (idempotent): result blocks that are recycled from call to
+    call, e.g. the node-shared arrays of parallel.Comm.shared_host_empty."""
+    r0, r1 = int(rows[0]), int(rows[1])
+    if r1 <= r0:
+        return True
+    view = torch.from_numpy(arr)[r0:r1]
+    return True if view.is_pinned() else _register(arr, view)
+
+
+def upload_rows_async(arr: np.ndarray, rows, device, stream: "torch.cuda.Stream"):
+    """Full-shape device tensor whose rows [rows[0], rows[1]) are being copied from the host array on `stream`; returns
+    (tensor, event recorded after the copy).  Rows outside the range stay uninitialised."""
+    a = np.ascontiguousarray(arr)
+    if a.dtype not in (np.uint8, np.uint16, np.float32):
+        raise TypeError(f"unsupported dtype {a.dtype}; expected uint8, uint16 or float32")
+    src = torch.from_numpy(a)
+    t = torch.empty(src.shape, dtype=src.dtype, device=device or "cuda")
+    r0, r1 = int(rows[0]), int(rows[1])
+    ev = torch.cuda.Event()
+    stream.wait_stream(torch.cuda.current_stream())      # the allocation above is ordered on the current stream
+    with torch.cuda.stream(stream):
+        if r1 > r0:
+            view = src[r0:r1]
+            pin_on_reuse(a, view)
+            t[r0:r1].copy_(view, non_blocking=True)
+        ev.record(stream)
+    return t, ev
+
+
+_COPY_STREAMS = {}
+
+
+def upload_rows(arr: np.ndarray, rows, device=None):
+    """upload_rows_async on this device's upload stream; returns (tensor, event) -- call wait_upload(event) on the
+    stream that reads the tensor, as late as possible."""
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    st = _COPY_STREAMS.get(dev)
+    if st is None:
+        st = _COPY_STREAMS[dev] = torch.cuda.Stream(dev)
+    return upload_rows_async(arr, rows, dev, st)
+
+
+def wait_upload(event):
+    if event is not None:
+        torch.cuda.current_stream().wait_event(event)
+
+
+def host_result(shape, dtype) -> np.ndarray:
+    """Fresh page-locked host array for a result (torch's caching host allocator recycles the block once the array dies)."""
+    tdt = dtype if isinstance(dtype, torch.dtype) else torch.from_numpy(np.empty(0, dtype)).dtype
+    return torch.empty(tuple(shape), dtype=tdt, pin_memory=True).numpy()
+
+
+class HostSink:
+    """Streams rows of a device tensor into a host array on a side stream while the kernels that follow keep running
+    (PCIe copies overlap compute).  push() orders the copy after everything enqueued so far on the current stream; a
+    later push() of the same rows overwrites an earlier one (copies on the side stream run in order)."""
+
+    def __init__(self, host: np.ndarray):
+        self.array = host
+        self._host = torch.from_numpy(host)
+        self._stream = torch.cuda.Stream()
+        self._keep = []
+
+    def push(self, dev: torch.Tensor, rows):
+        r0, r1 = int(rows[0]), int(rows[1])
+        if r1 <= r0:
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._stream.wait_event(ev)
+        with torch.cuda.stream(self._stream):
+            self._host[r0:r1].copy_(dev[r0:r1], non_blocking=True)
+        self._keep.append(dev)          # the source must outlive the copy
+
+    def wait(self):
+        self._stream.synchronize()
+        self._keep.clear()
+
+
+def mirror(arr: np.ndarray, dev: torch.Tensor) -> np.ndarray:
+    """Mark a result array READ-ONLY and remember the device tensor it was copied from for as long as the array lives
+    (see to_host(mirror=True))."""
+    arr.flags.writeable = False
+    key = id(arr)
+    _MIRRORS[key] = (weakref.ref(arr, lambda _r, key=key: _MIRRORS.pop(key, None)), dev)
+    return arr
 
 
 def pinned_like(arr: np.ndarray) -> np.ndarray:
@@ -295,8 +442,7 @@ def nmi_chunks(a: torch.Tensor, b: torch.Tensor, chunk: int) -> torch.Tensor:
     chunk = int(min(chunk, n))
     nchunks = -(-n // chunk)
     scores = torch.empty(nchunks, dtype=torch.float64, device=a.device)
-    ws = _bytes(lib.ma_nmi_workspace_bytes(n, chunk), a.device)
-    check(lib.ma_nmi_chunks(a.data_ptr(), b.data_ptr(), n, chunk, scores.data_ptr(), ws.data_ptr(), _stream()),
+    check(lib.ma_nmi_chunks(a.data_ptr(), b.data_ptr(), n, chunk, scores.data_ptr(), None, _stream()),
           "ma_nmi_chunks")
     return scores
 
@@ -394,7 +540,6 @@ def dog_quantize_rows(diff, h, w, diff_minmax, rows, out):
 
 def nmi_chunk_range(a, b, chunk, chunk_range, scores):
     n = a.numel()
-    ws = _bytes(lib.ma_nmi_workspace_bytes(n, int(chunk)), a.device)
     check(lib.ma_nmi_chunk_range(a.data_ptr(), b.data_ptr(), n, int(chunk), int(chunk_range[0]), int(chunk_range[1]),
-                                 scores.data_ptr(), ws.data_ptr(), _stream()), "ma_nmi_chunk_range")
+                                 scores.data_ptr(), None, _stream()), "ma_nmi_chunk_range")
     return scores

@@ -19,8 +19,6 @@ import torch
 from .. import ops, parallel
 from ..engine import Engine
 from ..shared_modules.img_checks import check_img_dims_match, check_img_is_2d_grey, check_img_is_provided
-from .flow_calc import TileFlowCalc
-from .warper import Warper
 
 
 class OptFlowRegistrator:
@@ -33,11 +31,11 @@ class OptFlowRegistrator:
         self.overlap = 100
         self.use_full_res_img = False
         self.use_dog = False
-        self._warper = Warper()
-        self._tile_flow_calc = TileFlowCalc()
         self.decisions: List[dict] = []  # per level: factor, mi_after, mi_before, better (diagnostic)
-        # numpy results are read-only and stay mirrored on the device (ops.to_host): handing the flow to
-        # Warper.flow then needs no upload.  Set False for a plain writeable array, as the reference returns.
+        # numpy results are READ-ONLY and stay mirrored on the device: handing the flow to Warper.flow then needs no
+        # upload.  The mirror holds the device copy of the flow (8 bytes per pixel of HBM, on several ranks this rank's
+        # band of it) for as long as the returned array is alive -- keep one flow per cycle alive and that many flows
+        # stay in HBM.  Set False for a plain writeable array without a device copy, as the reference returns.
         self.mirror_flow = True
         # multi-GPU only (parallel.init): False leaves a device-resident flow sharded -- each rank's tensor is
         # valid on its own band of tile rows, which is all Warper.warp() on the same ranks needs
@@ -71,18 +69,6 @@ class OptFlowRegistrator:
         self._mov_img = img
 
     # ------------------------------------------------------------------ helpers
-    def _init_warper(self):
-        self._warper = Warper()
-        self._warper.tile_size = self.tile_size
-        self._warper.overlap = self.overlap
-
-    def _init_tile_flow_calc(self):
-        self._tile_flow_calc = TileFlowCalc()
-        self._tile_flow_calc.tile_size = self.tile_size
-        self._tile_flow_calc.overlap = self.overlap
-        self._tile_flow_calc.num_iter = self.num_iterations
-        self._tile_flow_calc.win_size = self.overlap - (1 - self.overlap % 2)
-
     def get_dog_sigmas(self, pyr_factor: int) -> Tuple[int, int]:
         if pyr_factor > 16:
             return 1, 2
@@ -100,40 +86,37 @@ class OptFlowRegistrator:
         return ops.to_host(ops.dog_u8(ops.to_device(img)))
 
     # ------------------------------------------------------------------ the hot path
+    def _engine(self) -> Engine:
+        return Engine(self.tile_size, self.overlap, self.num_pyr_lvl, self.num_iterations, self.use_full_res_img,
+                      self.use_dog, comm=parallel.get(), contract_fma=not self.exact_arithmetic,
+                      corrected=self.corrected_composition)
+
     def register(self):
+        """(H, W, 2) float32 flow of mov_img onto ref_img (optflow_registrator.py:93-173).
+
+        numpy images -> numpy flow.  Host traffic is kept off the critical path: the images go up on a copy stream, the
+        rows of the flow come down while the device is still working on the rest.  Under a process group
+        (parallel.init, one process per GPU) every rank passes full-shape images, of which it reads and uploads only its
+        own rows, and every rank gets the full flow back: the array lives in node-shared memory and each rank fills in the
+        rows it computed over its own PCIe link.
+        CUDA tensors -> CUDA tensor (device-resident hand-off to Warper; see `gather_flow` for several ranks)."""
         check_img_is_provided(self._ref_img, "ref")
         check_img_is_provided(self._mov_img, "mov")
         check_img_dims_match(self._ref_img, self._mov_img)
-        host_result = not isinstance(self._ref_img, torch.Tensor)
-
-        self._init_tile_flow_calc()
-        self._init_warper()
-
-        ref = ops.to_device(self._ref_img)
-        mov = ops.to_device(self._mov_img, ref.device)
-        eng = Engine(self.tile_size, self.overlap, self.num_pyr_lvl, self.num_iterations, self.use_full_res_img,
-                     self.use_dog, comm=parallel.get(), contract_fma=not self.exact_arithmetic,
-                     corrected=self.corrected_composition)
-        eng.gather_flow = self.gather_flow or host_result
-        m_flow = eng.register(ref, mov)     # the coarse-to-fine loop, sharded over the ranks of parallel.get()
+        eng = self._engine()
+        if isinstance(self._ref_img, torch.Tensor):
+            ref = ops.to_device(self._ref_img)
+            mov = ops.to_device(self._mov_img, ref.device)
+            eng.gather_flow = self.gather_flow
+            m_flow = eng.register(ref, mov)     # the coarse-to-fine loop, sharded over the ranks of parallel.get()
+            self.decisions = eng.decisions
+            return m_flow
+        ref, mov = np.asarray(self._ref_img), np.asarray(self._mov_img)
+        for a in (ref, mov):
+            if a.dtype not in (np.uint8, np.uint16):
+                raise TypeError(f"unsupported image dtype {a.dtype}; expected uint8 or uint16")
+        flow, dev_flow = eng.register_host(ref, mov)
         self.decisions = eng.decisions
-        return ops.to_host(m_flow, mirror=self.mirror_flow) if host_result else m_flow
-
-    def register_sharded(self):
-        """Opt-in, beyond the reference, for several ranks (parallel.init) and host images: every rank uploads only the
-        rows of ref_img / mov_img it reads and downloads only its band of the flow, so the host<->device traffic is
-        spread over all ranks' PCIe links instead of funnelled through one.  ref_img / mov_img are full-shape arrays on
-        every rank (e.g. memory-mapped TIFF pages -- only this rank's rows are touched).
-        Returns (rows, flow): `flow` holds rows [rows[0], rows[1]) of the flow field; the device copy, valid on those rows
-        plus the overlap, stays in `self.device_flow` for Warper.warp_sharded()."""
-        check_img_is_provided(self._ref_img, "ref")
-        check_img_is_provided(self._mov_img, "mov")
-        check_img_dims_match(self._ref_img, self._mov_img)
-        self._init_tile_flow_calc()
-        self._init_warper()
-        eng = Engine(self.tile_size, self.overlap, self.num_pyr_lvl, self.num_iterations, self.use_full_res_img,
-                     self.use_dog, comm=parallel.get(), contract_fma=not self.exact_arithmetic,
-                     corrected=self.corrected_composition)
-        rows, flow, self.device_flow = eng.register_host_sharded(np.asarray(self._ref_img), np.asarray(self._mov_img))
-        self.decisions = eng.decisions
-        return rows, flow
+        if self.mirror_flow:
+            ops.mirror(flow, dev_flow)
+        return flow

@@ -22,31 +22,32 @@ class Warper:
         self._slicer_info = {}
 
     def warp(self):
-        host_result = not isinstance(self.image, torch.Tensor)
-        if host_result and parallel.get().world == 1 and isinstance(self.image, np.ndarray) and self.image.ndim == 2 \
-                and self.image.dtype in (np.uint8, np.uint16) and self.image.shape[0] >= 2 * self.tile_size:
-            # large host image, single GPU: stream tile rows up / through the kernel / down on three streams
-            flow = ops.to_device(self.flow)
-            image, self.image, self.flow = self.image, np.array([]), np.array([])
-            if tuple(flow.shape) != image.shape + (2,) or flow.dtype != torch.float32:
-                raise ValueError(f"flow must be float32 of shape {image.shape + (2,)}, got {flow.dtype} {tuple(flow.shape)}")
-            return ops.warp_tiles_host_streamed(image, flow, self.tile_size, self.overlap)
-        img = ops.to_device(self.image, self.flow.device if isinstance(self.flow, torch.Tensor) else None)
-        flow = ops.to_device(self.flow, img.device)
-        self.image = np.array([])
+        image, flow = self.image, self.flow
+        self.image = np.array([])           # the reference blanks its inputs (warper.py:41,45)
         self.flow = np.array([])
-        out = Engine(self.tile_size, self.overlap, comm=parallel.get()).warp(img, flow)
-        return ops.to_host(out) if host_result else out
-
-    def warp_sharded(self):
-        """Opt-in companion of OptFlowRegistrator.register_sharded() for several ranks: `image` is a full-shape host array
-        (only the rows this rank's tile windows read are uploaded), `flow` the device flow `reg.device_flow`.
-        Returns (rows, warped): rows [rows[0], rows[1]) of the warped image, computed and downloaded by this rank."""
-        if not isinstance(self.flow, torch.Tensor):
-            raise TypeError("warp_sharded() needs the device flow of register_sharded() (reg.device_flow)")
-        image, flow = np.asarray(self.image), self.flow
-        self.image = np.array([])
-        self.flow = np.array([])
-        if tuple(flow.shape) != image.shape + (2,) or flow.dtype != torch.float32:
+        comm = parallel.get()
+        if isinstance(image, torch.Tensor):
+            flow = ops.to_device(flow, image.device)
+            return Engine(self.tile_size, self.overlap, comm=comm).warp(ops.to_device(image), flow)
+        image = np.asarray(image)
+        if image.ndim != 2 or image.dtype not in (np.uint8, np.uint16):
+            raise TypeError(f"unsupported image: dtype {image.dtype}, {image.ndim} dimensions; expected 2-D uint8 or uint16")
+        if tuple(flow.shape) != image.shape + (2,) or str(flow.dtype).replace("torch.", "") != "float32":
             raise ValueError(f"flow must be float32 of shape {image.shape + (2,)}, got {flow.dtype} {tuple(flow.shape)}")
-        return Engine(self.tile_size, self.overlap, comm=parallel.get()).warp_host_sharded(image, flow)
+        eng = Engine(self.tile_size, self.overlap, comm=comm)
+        if comm.world == 1:
+            flow_d = ops.to_device(flow)
+            if image.shape[0] >= 2 * self.tile_size:
+                # large host image: tile rows stream up / through the kernel / down on three streams
+                return ops.warp_tiles_host_streamed(image, flow_d, self.tile_size, self.overlap)
+            return ops.to_host(eng.warp(ops.to_device(image, flow_d.device), flow_d))
+        # several ranks: each uploads the rows its tile windows read, warps its band and fills its rows of the
+        # node-shared result.  A flow that is not already on the devices is uploaded the same way, rows only.
+        if isinstance(flow, torch.Tensor):
+            flow_d = flow
+        else:
+            flow_d = ops.mirrored(flow)
+            if flow_d is None:
+                flow_d, ev = ops.upload_rows(np.asarray(flow), eng.flow_rows_needed(image.shape))
+                ops.wait_upload(ev)
+        return eng.warp_host(image, flow_d)

@@ -5,8 +5,12 @@ box, gloo in the CPU tests).  The path shards by tile rows: every
 image rows it owns, halo rows are exchanged point-to-point, the few global scalars (DoG min/max, NMI
 chunk scores) are all-reduced, and the final flow / image is gathered band by band.  With a world of 1
 every function here is a no-op, so the single-GPU path runs the very same engine code."""
+import os
+import tempfile
+import weakref
 from typing import List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -226,6 +230,58 @@ class Comm:
         if self.world > 1:
             dist.broadcast(self._wire(t), src=self._global[src], group=self.group)
         return t
+
+
+    # -- node-shared host memory ----------------------------------------------------------------
+    def barrier(self):
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+    def shared_host_empty(self, shape, dtype) -> np.ndarray:
+        """Host array of `shape` that every rank of the (single-node) group maps to the SAME pages (a file in /dev/shm
+        created by rank 0 and unlinked once everybody has mapped it).  This is how the drop-in numpy API returns a full
+        (H, W, 2) flow / (H, W) image on every rank although each rank downloads only its own band over its own PCIe
+        link.  Collective: every rank must call it with the same arguments in the same order.  Blocks are recycled once
+        the array handed out earlier is dead on every rank."""
+        shape, dtype = tuple(int(v) for v in shape), np.dtype(dtype)
+        if self.world == 1:
+            return np.empty(shape, dtype)
+        key = (shape, dtype.str)
+        pool = self.__dict__.setdefault("_shared_pool", {}).setdefault(key, [])
+        if pool:
+            free = torch.tensor([1 if e["ref"] is None or e["ref"]() is None else 0 for e in pool], dtype=torch.int32)
+            if self.backend == "nccl":
+                free = free.cuda()
+            dist.all_reduce(free, op=dist.ReduceOp.MIN, group=self.group)
+            for e, ok in zip(pool, free.tolist()):
+                if ok:
+                    return self._hand_out(e)
+        name = [None]
+        if self.rank == 0:
+            nbytes = int(np.prod(shape)) * dtype.itemsize
+            root = "/dev/shm" if os.path.isdir("/dev/shm") and _free_bytes("/dev/shm") > nbytes + (1 << 30) else tempfile.gettempdir()
+            seq = self.__dict__["_shared_seq"] = self.__dict__.get("_shared_seq", 0) + 1
+            name[0] = os.path.join(root, f"microaligner_b200_{os.getpid()}_{seq}.shared")
+            np.memmap(name[0], dtype=dtype, mode="w+", shape=shape).flush()
+        dist.broadcast_object_list(name, src=self._global[0], group=self.group)
+        mm = np.memmap(name[0], dtype=dtype, mode="r+", shape=shape)
+        self.barrier()
+        if self.rank == 0:
+            os.unlink(name[0])          # the mappings keep the pages alive
+        entry = {"mm": mm, "ref": None}
+        pool.append(entry)
+        return self._hand_out(entry)
+
+    @staticmethod
+    def _hand_out(entry) -> np.ndarray:
+        arr = np.asarray(entry["mm"]).view(np.ndarray)
+        entry["ref"] = weakref.ref(arr)
+        return arr
+
+
+def _free_bytes(path: str) -> int:
+    import shutil
+    return shutil.disk_usage(path).free
 
 
 _COMM = Comm(None)

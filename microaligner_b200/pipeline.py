@@ -12,7 +12,9 @@ max-projection runs on the device, and page uploads / warps / downloads are doub
 streams.  TIFF / OME-XML handling is out of scope (tifffile is not part of this environment): pages come
 from a *page provider* -- any mapping  cycle -> channel -> z -> 2-D uint8/uint16 array (numpy or CUDA
 tensor; values may be callables returning the array for lazy loading) -- and results go to a *sink*
-callable(cycle, channel, z, image: np.ndarray)."""
+callable(cycle, channel, z_index, image: np.ndarray), z_index = position of the plane among the channel's planes
+(the reference's datasets use 1-based z keys but write plane z_id = 0, 1, ...: __main__.py:296-300).
+The file-based entry point with the reference's YAML / TIFF handling is microaligner_b200/__main__.py."""
 from typing import Callable, Dict, Mapping, Optional, Sequence, Union
 
 import numpy as np
@@ -70,15 +72,15 @@ def warp_and_save_pages(sink, cyc, ch, flow: torch.Tensor, pages: Mapping[int, P
     streams = [torch.cuda.Stream(), torch.cuda.Stream()]
     cur = torch.cuda.current_stream()
     pending = []
-    for i, (z, page) in enumerate(pages.items()):
-        s = streams[i % 2]
+    for z_id, page in enumerate(pages.values()):      # the sink gets the plane INDEX, like mm[0, ch, z_id] (__main__.py:296-300)
+        s = streams[z_id % 2]
         s.wait_stream(cur)
         with torch.cuda.stream(s):
             img = ops.to_device(_load(page), flow.device)
             out = eng.warp(img, flow)
             host = torch.empty(out.shape, dtype=out.dtype, device="cpu", pin_memory=True)
             host.copy_(out, non_blocking=True)
-        pending.append((z, s, host, img, out))
+        pending.append((z_id, s, host, img, out))
         if len(pending) > 1:
             z0, s0, h0, _, _ = pending.pop(0)
             s0.synchronize()
@@ -145,9 +147,9 @@ def register_and_save_ofreg_imgs(dataset: Dataset, ref_channel: Union[str, Mappi
             ref_img = max_project_pages(zplanes)
             _say(f"Saving Cycle {cyc} [{cyc_id + 1}/{ncycles}]")
             for ch, pages in dataset[cyc].items():
-                for z, page in pages.items():
+                for z_id, page in enumerate(pages.values()):
                     p = _load(page)
-                    sink(cyc, ch, z, p.cpu().numpy() if isinstance(p, torch.Tensor) else np.asarray(p))
+                    sink(cyc, ch, z_id, p.cpu().numpy() if isinstance(p, torch.Tensor) else np.asarray(p))
             continue
         mov_img = max_project_pages(zplanes)
         ofreg.ref_img, ofreg.mov_img = ref_img, mov_img      # device tensors: the flow stays on the GPU

@@ -368,6 +368,24 @@ def memmap(path, shape: Sequence[int], dtype, description: Optional[str] = None,
     return np.memmap(os.fspath(path), dtype=dtype, mode="r+", offset=data_off, shape=shape)
 
 
+def memmap_existing(path, shape: Sequence[int], dtype) -> np.memmap:
+    """Map the pixel block of a file written by memmap() (contiguous, uncompressed pages) for reading and writing --
+    how the other ranks of a multi-GPU run open the output file rank 0 created."""
+    shape = tuple(int(s) for s in shape)
+    with TiffFile(path) as tf:
+        pages = tf.pages
+        n = int(np.prod(shape[:-2])) if len(shape) > 2 else 1
+        if len(pages) != n or pages[0].shape != shape[-2:] or not all(p.is_contiguous for p in pages):
+            raise TiffFormatError(f"{path} does not hold {n} contiguous pages of shape {shape[-2:]}")
+        first, nbytes = pages[0].offsets[0], pages[0].nbytes
+        if any(p.offsets[0] != first + i * nbytes for i, p in enumerate(pages)):
+            raise TiffFormatError(f"{path}: pages are not back to back")
+        if pages[0].dtype.newbyteorder("=") != np.dtype(dtype).newbyteorder("="):
+            raise TiffFormatError(f"{path}: dtype {pages[0].dtype} does not match {np.dtype(dtype)}")
+        dt = pages[0].dtype
+    return np.memmap(os.fspath(path), dtype=dt, mode="r+", offset=first, shape=shape)
+
+
 def imwrite(path, data: np.ndarray, description: Optional[str] = None):
     mm = memmap(path, data.shape, data.dtype, description)
     mm[...] = data

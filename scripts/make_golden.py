@@ -25,7 +25,35 @@ def versions():
     return dict(cv2=cv2.__version__, sklearn=sklearn.__version__, numpy=np.__version__)
 
 
+def pipeline_goldens(v):
+    """8. the YAML / TIFF pipeline: the unmodified reference's main() (__main__.py:624-642 -> run_opt_flow_reg :534-609 ->
+    register_and_save_ofreg_imgs :320-437) on the miniature datasets of tests/pipeline_data.py, its TIFF I/O served by the
+    tifffile stub of oracle/ref_shim.py."""
+    import tempfile
+    from tests import pipeline_data as pd
+    m = ref_shim.load_pipeline()
+    for layout in ("per_image", "stack"):
+        tmp = tempfile.mkdtemp()
+        cfg, out_dir = pd.write_inputs(tmp, layout)
+        buf, old = io.StringIO(), sys.argv
+        sys.argv = ["microaligner", cfg]
+        try:
+            with contextlib.redirect_stdout(buf):
+                m.main()
+        finally:
+            sys.argv = old
+        pixels, desc = pd.read_result(out_dir)
+        np.savez_compressed(os.path.join(OUT, f"pipeline_{layout}.npz"), pixels=pixels, description=desc,
+                            stdout=buf.getvalue().replace(tmp, "<TMP>"), **v)
+
+
 def main():
+    if "--only-pipeline" in sys.argv:
+        os.makedirs(OUT, exist_ok=True)
+        pipeline_goldens(versions())
+        for f in sorted(os.listdir(OUT)):
+            print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
+        return
     mod = ref_shim.load()
     import importlib
     fc = importlib.import_module("microaligner.optflow_reg.flow_calc")
@@ -112,6 +140,7 @@ def main():
             ofr.check_if_higher_similarity = old
     np.savez_compressed(os.path.join(OUT, "forced_decisions.npz"), ref=ref, mov=mov, num_pyr_lvl=2, num_iterations=1,
                         tile_size=120, overlap=16, **forced, **v)
+    pipeline_goldens(v)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
 

@@ -118,7 +118,7 @@ def test_sharded_engine_corner_cases(tmp_path, world, case, corrected):
         assert np.array_equal(got["flow"], want_flow) and np.array_equal(got["img"], want_img), f"rank {r} differs"
 
 
-def _worker_host_sharded(rank, world, port, case, tmp):
+def _worker_host(rank, world, port, case, tmp):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from microaligner_b200 import engine, parallel
@@ -130,31 +130,75 @@ def _worker_host_sharded(rank, world, port, case, tmp):
         ref, mov = synth_pair(shape[0], shape[1], 3, dtype, amp=2.0, period=160.0)
         eng = engine.Engine(kw["tile_size"], kw["overlap"], kw["num_pyr_lvl"], kw["num_iterations"], kw["use_full_res_img"],
                             kw["use_dog"], comm=parallel.get(), log=lambda *a: None)
-        rows, flow_rows, flow_dev = eng.register_host_sharded(ref, mov)
-        wrows, img_rows = eng.warp_host_sharded(mov, flow_dev)
-        np.savez(os.path.join(tmp, f"r{rank}.npz"), rows=np.array(rows), flow=flow_rows, wrows=np.array(wrows), img=img_rows,
-                 need=np.array(eng.full_input_rows(ref.shape)))
+        for rep in range(2):            # the second round reuses the node-shared result blocks of the first
+            flow, flow_dev = eng.register_host(ref, mov)
+            img = eng.warp_host(mov, flow_dev)
+            np.savez(os.path.join(tmp, f"r{rank}_{rep}.npz"), flow=flow, img=img, need=np.array(eng.full_input_rows(ref.shape)))
+            del flow, img
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.parametrize("world", [2, 3])
 @pytest.mark.parametrize("case", list(CASES))
-def test_sharded_host_io(tmp_path, case, world):
-    """register_host_sharded / warp_host_sharded: every rank uploads only the rows of ref / mov / image it reads (the rest
-    of its device buffers is garbage) and downloads only its band; the bands of all ranks tile the single-rank result."""
+def test_host_io_on_several_ranks(tmp_path, case, world):
+    """register_host / warp_host: every rank uploads only the rows of ref / mov / image it reads (the rest of its device
+    buffers is garbage) and delivers only its own rows, yet every rank ends up with the complete single-rank result
+    (node-shared result arrays)."""
     shape, dtype, kw = CASES[case]
     ref, mov = synth_pair(shape[0], shape[1], 3, dtype, amp=2.0, period=160.0)
     want_flow, want_img, _ = _run(ref, mov, kw)
-    mp.spawn(_worker_host_sharded, args=(world, _free_port(), case, str(tmp_path)), nprocs=world, join=True)
-    flow_cover, img_cover = np.zeros(shape[0], int), np.zeros(shape[0], int)
+    mp.spawn(_worker_host, args=(world, _free_port(), case, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
-        got = np.load(tmp_path / f"r{r}.npz")
-        (a, b), (c, d) = got["rows"], got["wrows"]
-        assert np.array_equal(got["flow"], want_flow[a:b]), f"rank {r}: flow rows {a}:{b} differ"
-        assert np.array_equal(got["img"], want_img[c:d]), f"rank {r}: warped rows {c}:{d} differ"
-        flow_cover[a:b] += 1
-        img_cover[c:d] += 1
+        for rep in range(2):
+            got = np.load(tmp_path / f"r{r}_{rep}.npz")
+            assert np.array_equal(got["flow"], want_flow), f"rank {r} round {rep}: flow differs"
+            assert np.array_equal(got["img"], want_img), f"rank {r} round {rep}: warped image differs"
         if case == "tiled levels, dog" and world == 3:       # every level sharded: a real share, not the whole image
             assert got["need"][1] - got["need"][0] < shape[0]
-    assert (flow_cover >= 1).all() and (img_cover >= 1).all()
+
+
+STREAM_CASE = ((640, 530), np.uint16, dict(tile_size=100, overlap=16, num_pyr_lvl=1, num_iterations=1, use_full_res_img=True,
+                                           use_dog=False))
+
+
+@pytest.mark.parametrize("forced", [None, (True, True), (True, False), (False, True)])
+def test_speculative_streaming_on_one_rank(forced):
+    """One GPU, host result: the last level's Farneback runs in groups of tile rows, each complete tile row is merged and
+    delivered right behind it (sink log), and the delivered array equals the plain device-path result -- also when the
+    gate rejects the last level and everything is delivered again from the flow that is returned instead."""
+    from microaligner_b200 import engine, parallel
+    from tests import mock_ops
+    shape, dtype, kw = STREAM_CASE
+    ref, mov = synth_pair(shape[0], shape[1], 5, dtype, amp=2.0, period=160.0)
+    saved = engine.ops, engine.torch
+    engine.ops, engine.torch = mock_ops, _PoisonTorch()
+    try:
+        def make():
+            e = engine.Engine(kw["tile_size"], kw["overlap"], kw["num_pyr_lvl"], kw["num_iterations"], kw["use_full_res_img"],
+                              kw["use_dog"], comm=parallel.Comm(None), log=lambda *a: None)
+            e.force_decisions = forced
+            e.group_tiles = 6            # one tile row per group
+            return e
+        want = make().register(torch.from_numpy(ref), torch.from_numpy(mov)).numpy().copy()
+        sinks = []
+        real = mock_ops.HostSink
+        mock_ops.HostSink = lambda host: sinks.append(real(host)) or sinks[-1]
+        try:
+            eng = make()
+            flow, dev = eng.register_host(ref, mov)
+        finally:
+            mock_ops.HostSink = real
+        assert np.array_equal(flow, want) and np.array_equal(dev.numpy(), want)
+        log = sinks[0].log
+        ny = -(-shape[0] // kw["tile_size"])
+        speculated = [r for r in log if r != (0, shape[0])]
+        assert len(speculated) >= 2 and speculated[0][0] == 0 and speculated[-1][1] == shape[0], log
+        assert all(a[1] == b[0] for a, b in zip(speculated, speculated[1:])), log       # contiguous, in order
+        assert ny >= 6
+        if forced is not None and not forced[-1]:
+            assert log[-1] == (0, shape[0])          # rejected level: everything delivered again
+        else:
+            assert log == speculated
+    finally:
+        engine.ops, engine.torch = saved

@@ -39,10 +39,10 @@ def _run(ref, mov, kw):
     return flow.cpu().numpy(), w.warp().cpu().numpy(), [d["better"] for d in reg.decisions]
 
 
-def _worker(rank, world, port, case_id, tmp, local_pyramid=False):
+def _worker(rank, world, port, case_id, tmp, gathered_pyramid=False):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
-    if local_pyramid:
-        os.environ["MA_LOCAL_PYRAMID"] = "1"    # read by Engine.__init__
+    if gathered_pyramid:
+        os.environ["MA_LOCAL_PYRAMID"] = "0"    # read by Engine.__init__: pyramid levels computed in slices and gathered
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from microaligner_b200 import parallel
     parallel.init(dist.group.WORLD)
@@ -79,19 +79,22 @@ def test_sharded_equals_single(cuda, tmp_path, case_id, world):
 
 @pytest.mark.timeout(600)
 @pytest.mark.parametrize("world", [2, 3])
-def test_sharded_local_pyramid_equals_single(cuda, tmp_path, world):
+def test_sharded_gathered_pyramid_equals_single(cuda, tmp_path, world):
+    """The band-local pyramid is the default (LOCAL_CASE has every level tiled, so it really leaves rows uncomputed);
+    MA_LOCAL_PYRAMID=0 selects the variant that computes every level in slices and gathers it."""
     shape, dtype, kw = LOCAL_CASE
     ref, mov = synth_pair(shape[0], shape[1], 7, dtype)
     want_flow, want_img, want_dec = _run(ref, mov, kw)
-    mp.spawn(_worker, args=(world, _free_port(), -1, str(tmp_path), True), nprocs=world, join=True)
-    for r in range(world):
-        got = np.load(tmp_path / f"r{r}.npz")
-        assert list(got["dec"]) == want_dec
-        assert np.array_equal(got["flow"], want_flow), f"rank {r}: flow differs"
-        assert np.array_equal(got["img"], want_img), f"rank {r}: warped image differs"
+    for gathered in (False, True):
+        mp.spawn(_worker, args=(world, _free_port(), -1, str(tmp_path), gathered), nprocs=world, join=True)
+        for r in range(world):
+            got = np.load(tmp_path / f"r{r}.npz")
+            assert list(got["dec"]) == want_dec
+            assert np.array_equal(got["flow"], want_flow), f"rank {r}: flow differs (gathered pyramid: {gathered})"
+            assert np.array_equal(got["img"], want_img), f"rank {r}: warped image differs (gathered pyramid: {gathered})"
 
 
-def _worker_host_sharded(rank, world, port, tmp):
+def _worker_host(rank, world, port, tmp):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from microaligner_b200 import OptFlowRegistrator, Warper, parallel
@@ -99,33 +102,38 @@ def _worker_host_sharded(rank, world, port, tmp):
     try:
         shape, dtype, kw = LOCAL_CASE
         ref, mov = synth_pair(shape[0], shape[1], 7, dtype)
-        reg = OptFlowRegistrator()
-        for k, v in kw.items():
-            setattr(reg, k, v)
-        reg.ref_img, reg.mov_img = ref, mov
-        with contextlib.redirect_stdout(io.StringIO()):
-            rows, flow = reg.register_sharded()
-        w = Warper()
-        w.tile_size, w.overlap = kw["tile_size"], kw["overlap"]
-        w.image, w.flow = mov, reg.device_flow
-        wrows, img = w.warp_sharded()
-        np.savez(os.path.join(tmp, f"r{rank}.npz"), rows=np.array(rows), flow=flow, wrows=np.array(wrows), img=img)
+        for rep in range(2):       # the second round reuses the node-shared result blocks and the page-locked inputs
+            reg = OptFlowRegistrator()
+            for k, v in kw.items():
+                setattr(reg, k, v)
+            reg.ref_img, reg.mov_img = ref, mov          # numpy in ...
+            with contextlib.redirect_stdout(io.StringIO()):
+                flow = reg.register()                    # ... full numpy flow out, on every rank
+            w = Warper()
+            w.tile_size, w.overlap = kw["tile_size"], kw["overlap"]
+            w.image, w.flow = mov, flow
+            img = w.warp()
+            # a plain (un-mirrored) copy of the flow is uploaded band-wise instead
+            w.image, w.flow = mov, flow.copy()
+            img2 = w.warp()
+            np.savez(os.path.join(tmp, f"r{rank}_{rep}.npz"), flow=flow, img=img, img2=img2)
+            del flow, img, img2
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.timeout(600)
 @pytest.mark.parametrize("world", [2, 3])
-def test_sharded_host_io_equals_single(cuda, tmp_path, world):
+def test_numpy_api_on_several_ranks(cuda, tmp_path, world):
+    """The drop-in numpy API under a process group: every rank uploads only its rows and downloads only its rows, and
+    every rank gets the complete flow / warped image (node-shared result arrays)."""
     shape, dtype, kw = LOCAL_CASE
     ref, mov = synth_pair(shape[0], shape[1], 7, dtype)
     want_flow, want_img, _ = _run(ref, mov, kw)
-    mp.spawn(_worker_host_sharded, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
-    covered = np.zeros(shape[0], int)
+    mp.spawn(_worker_host, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
-        got = np.load(tmp_path / f"r{r}.npz")
-        (a, b), (c, d) = got["rows"], got["wrows"]
-        assert np.array_equal(got["flow"], want_flow[a:b]), f"rank {r}: flow rows differ"
-        assert np.array_equal(got["img"], want_img[c:d]), f"rank {r}: warped rows differ"
-        covered[a:b] += 1
-    assert (covered == 1).all()
+        for rep in range(2):
+            got = np.load(tmp_path / f"r{r}_{rep}.npz")
+            assert got["flow"].shape == want_flow.shape and np.array_equal(got["flow"], want_flow), f"rank {r}/{rep}: flow differs"
+            assert np.array_equal(got["img"], want_img), f"rank {r}/{rep}: warped image differs"
+            assert np.array_equal(got["img2"], want_img), f"rank {r}/{rep}: warped image (uploaded flow) differs"
