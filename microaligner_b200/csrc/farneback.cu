@@ -276,19 +276,20 @@ __global__ void __launch_bounds__(PM_WARPS * 32) fb_polyexp_march_kernel(const T
     const bool writer = lane >= 2 && lane < 2 + PM_OUTW && colin;
     const T* pm = mov + (ox + x);
     const T* pr = ref + (ox + x);
-    auto load = [&](int v, float& a, float& c) {
+    // raw pixels stay integers while they are in flight: converting at load time would make every load wait for its data
+    auto load = [&](int v, T& a, T& c) {
         const int gy = oy + reflect101(v, Sh);
-        a = 0.0f;
-        c = 0.0f;
+        a = 0;
+        c = 0;
         if (colok && (unsigned)gy < (unsigned)g.h) {
-            a = (float)__ldg(reinterpret_cast<const T*>(reinterpret_cast<const char*>(pm) + (size_t)gy * pitch));
-            c = (float)__ldg(reinterpret_cast<const T*>(reinterpret_cast<const char*>(pr) + (size_t)gy * pitch));
+            a = __ldg(reinterpret_cast<const T*>(reinterpret_cast<const char*>(pm) + (size_t)gy * pitch));
+            c = __ldg(reinterpret_cast<const T*>(reinterpret_cast<const char*>(pr) + (size_t)gy * pitch));
         }
     };
     float th0[2] = {0, 0}, th1[2] = {0, 0}, th2[2] = {0, 0}, P0[2] = {0, 0}, P1[2] = {0, 0}, P2[2] = {0, 0};
     // kPmDepth - 1 rows are in flight behind the row being processed (one row was not enough to cover the DRAM latency:
     // ncu showed the kernel waiting on its loads at 38 % of DRAM peak); the queue rotates through static indices
-    float q[kPmDepth][2];
+    T q[kPmDepth][2];
     const int vend = yb + 2;
 #pragma unroll
     for (int k = 0; k < kPmDepth - 1; ++k)
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(PM_WARPS * 32) fb_polyexp_march_kernel(const T
         const int v = vb + k;
         if (v >= vend) break;
         if (v + kPmDepth - 1 < vend) load(v + kPmDepth - 1, q[(k + kPmDepth - 1) % kPmDepth][0], q[(k + kPmDepth - 1) % kPmDepth][1]);
-        float raw[2] = {q[k][0], q[k][1]};
+        float raw[2] = {(float)q[k][0], (float)q[k][1]};
 #pragma unroll
         for (int im = 0; im < 2; ++im) {
             const float l = __shfl_sync(0xffffffffu, raw[im], srcL), r = __shfl_sync(0xffffffffu, raw[im], srcR);

@@ -42,8 +42,14 @@ def main():
         parallel.init(None)
         f0, i0, d0 = run(ref, mov, kw)
         same = bool(torch.equal(f0, f1)) and bool(torch.equal(i0, i1)) and d0 == d1
-        print(f"rank {dist.get_rank()}/{dist.get_world_size()} {kw}: decisions {d1} identical={same}", flush=True)
-        ok = ok and same
+        # the drop-in numpy API under the process group: rows up / rows down per rank, full node-shared arrays back
+        parallel.init(dist.group.WORLD)
+        f2, i2, d2 = run(ref_h, mov_h, kw)
+        same_np = bool(np.array_equal(f2, f0.cpu().numpy())) and bool(np.array_equal(i2, i0.cpu().numpy())) and d2 == d0
+        del f2, i2
+        print(f"rank {dist.get_rank()}/{dist.get_world_size()} {kw}: decisions {d1} device path identical={same} "
+              f"numpy API identical={same_np}", flush=True)
+        ok = ok and same and same_np
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
