@@ -329,27 +329,39 @@ class Engine:
                 fb_mov = dogs[2] if self.use_dog else mov_l
                 del dogs, items
             this_flow = torch.empty((L.h, L.w, 2), dtype=torch.float32, device=ref.device)
-            # Speculative tail of the LAST level on one GPU: if the gate accepts this level -- it nearly always does --
-            # the result is merge(m_flow, this_flow), which is per tile.  So the Farneback tiles run one group of tile
-            # rows at a time, every tile row whose window is complete is merged right behind it, and its rows start
-            # their way to the host while the next group is computed.  Should the gate reject the level, the rows are
-            # simply sent again from the flow that is returned instead.
-            speculate = (sink is not None and self.stream_groups and L.tiled and not L.sharded and comm.world == 1
-                         and lvl == num_lvl - 1 and lvl > 0 and self.full_res and not self.corrected)
-            merged, merged_hi = None, 0
+            # Speculative tail of the LAST level: if the gate accepts this level -- it nearly always does -- the result is
+            # merge(m_flow, this_flow), which is per tile.  So this rank's Farneback tiles run one group of tile rows at a
+            # time, every tile row of its band whose window it has completed itself is merged right behind it, and those rows
+            # start their way to the host while the next group is computed.  The tile rows next to another rank's tiles wait
+            # for the exchange, as before.  Should the gate reject the level, all rows are simply sent again from the flow
+            # that is returned instead.
+            speculate = (sink is not None and self.stream_groups and L.tiled and lvl == num_lvl - 1 and lvl > 0
+                         and self.full_res and not self.corrected)
+            merged, m_lo, m_hi = None, 0, 0                        # tile rows [m_lo, m_hi) of `merged` are done and sent
             with self.phase("farneback" if L.tiled else "farneback(untiled level)"):
                 if speculate:
                     merged = torch.empty_like(this_flow)
-                    step = max(1, -(-self.group_tiles // L.nx))     # tile rows per group
-                    for i0 in range(0, L.ny, step):
-                        i1 = min(i0 + step, L.ny)
-                        ops.farneback_tiles(fb_mov, fb_ref, T, ov, self.win, self.iters, (i0 * L.nx, i1 * L.nx), out=this_flow,
-                                            contract_fma=self.contract_fma)
-                        ready_hi = i1 if i1 == L.ny else i1 - 1     # tile row i reads rows up to (i + 1) T + ov
-                        if ready_hi > merged_hi:
-                            ops.merge_flows_tile_rows(m_flow, this_flow, T, ov, (merged_hi, ready_hi), merged)
-                            sink.push(merged, _clip(merged_hi * T, ready_hi * T, L.h))
-                            merged_hi = ready_hi
+                    t0, t1 = L.fb_tiles[L.rank]
+                    ba, bb = L.tile_rows[L.rank]
+                    ia, ib = -(-t0 // L.nx), t1 // L.nx            # tile rows [ia, ib) are computed entirely by this rank
+                    fb = lambda a, b: b > a and ops.farneback_tiles(fb_mov, fb_ref, T, ov, self.win, self.iters, (a, b),   # noqa: E731
+                                                                    out=this_flow, contract_fma=self.contract_fma)
+                    if ib <= ia:                                   # less than one whole tile row: nothing to stream
+                        fb(t0, t1)
+                    else:
+                        fb(t0, ia * L.nx)                          # tail of the previous rank's last tile row
+                        # a tile row reads this_flow up to `ov` rows into both neighbouring tile rows
+                        m_lo = m_hi = max(ba, ia + (1 if ia > 0 else 0))
+                        step = max(1, -(-self.group_tiles // L.nx))     # tile rows per group
+                        for i0 in range(ia, ib, step):
+                            i1 = min(i0 + step, ib)
+                            fb(i0 * L.nx, i1 * L.nx)
+                            ready_hi = min(bb, i1 if i1 == L.ny else i1 - 1)
+                            if ready_hi > m_hi:
+                                ops.merge_flows_tile_rows(m_flow, this_flow, T, ov, (m_hi, ready_hi), merged)
+                                sink.push(merged, _clip(m_hi * T, ready_hi * T, L.h))
+                                m_hi = ready_hi
+                        fb(ib * L.nx, t1)                          # head of the next rank's first tile row
                 elif L.tiled:
                     ops.farneback_tiles(fb_mov, fb_ref, T, ov, self.win, self.iters, L.fb_tiles[L.rank], out=this_flow,
                                         contract_fma=self.contract_fma)
@@ -391,8 +403,13 @@ class Engine:
                 elif lvl == num_lvl - 1:
                     if merged is None:
                         merged = self._merge(m_flow, this_flow, L)
-                    else:
-                        sink = None                      # every row of the result is already on its way to the host
+                    else:                                # the tile rows of the band that were not merged speculatively
+                        ba, bb = L.tile_rows[L.rank]
+                        for a, b in ((ba, min(m_lo, bb)), (max(m_hi, ba), bb)) if m_hi > m_lo else ((ba, bb),):
+                            if b > a:
+                                ops.merge_flows_tile_rows(m_flow, this_flow, T, ov, (a, b), merged)
+                                sink.push(merged, _clip(a * T, b * T, L.h))
+                        sink = None                      # every row of the result is on its way to the host
                     m_flow, m_layout = merged, L
                     if not self.full_res:
                         m_flow, m_layout = self._upscale_to_full(merged, L, full, factor)
@@ -534,19 +551,22 @@ class Engine:
         L = LevelLayout(img.shape[0], img.shape[1], self.T, self.ov, comm)
         if L.sharded and L.ny < 2:      # a single row of tiles: warp() is replicated, so it needs the whole flow
             comm.gather_rows(flow, L.bands)
-        need = _clip(band[0] - self.ov, band[1] + self.ov, img.shape[0]) if band[1] > band[0] else (0, 0)
-        img_d, ev = ops.upload_rows(img, need, flow.device)
-        ops.wait_upload(ev)
-        out_d = self.warp(img_d, flow, gather=False)
-        rows = band if (comm.world > 1 and L.ny >= 2) else self.result_rows(None, img.shape[0])
+        sharded = comm.world > 1 and L.ny >= 2
+        rows = band if sharded else self.result_rows(None, img.shape[0])
         if comm.world > 1:
             out = comm.shared_host_empty(img.shape, img.dtype)
             ops.pin_rows(out, rows)
         else:
             out = ops.host_result(img.shape, img.dtype)
-        sink = ops.HostSink(out)
-        sink.push(out_d, rows)
-        sink.wait()
+        if sharded:      # tile rows of the band stream up / through the kernel / down on three streams
+            ops.warp_tiles_host_streamed(img, flow, self.T, self.ov, rows=band, out=out)
+        else:
+            img_d, ev = ops.upload_rows(img, (0, img.shape[0]), flow.device)
+            ops.wait_upload(ev)
+            out_d = self.warp(img_d, flow, gather=False)
+            sink = ops.HostSink(out)
+            sink.push(out_d, rows)
+            sink.wait()
         comm.barrier()
         return out
 

@@ -119,6 +119,16 @@ _REGISTERED = {}  # (address, nbytes) -> True for ranges page-locked with cudaHo
 PIN_MIN_BYTES = 32 << 20
 
 
+def _clear_cuda_error():
+    import ctypes
+    for name in ("libcudart.so.12", "libcudart.so"):
+        try:
+            ctypes.CDLL(name).cudaGetLastError()
+            return
+        except OSError:
+            continue
+
+
 def _unregister(key):
     if _REGISTERED.pop(key, None):
         try:
@@ -132,7 +142,9 @@ def _register(arr: np.ndarray, view: torch.Tensor) -> bool:
     if key in _REGISTERED:
         return True
     if int(torch.cuda.cudart().cudaHostRegister(key[0], key[1], 0)) != 0:
-        torch.cuda.cudart().cudaGetLastError()
+        # not page-lockable (e.g. a disk-backed mapping): copies from / to this range stay staged.  The sticky error
+        # code is cleared through the runtime library the process already has loaded.
+        _clear_cuda_error()
         _SEEN[key] = -(1 << 30)        # do not try again
         return False
     _REGISTERED[key] = True
@@ -304,27 +316,35 @@ def warp_tiles(img: torch.Tensor, flow: torch.Tensor, tile_size: int, overlap: i
     return out
 
 
-def warp_tiles_host_streamed(image: np.ndarray, flow: torch.Tensor, tile_size: int, overlap: int) -> np.ndarray:
+def warp_tiles_host_streamed(image: np.ndarray, flow: torch.Tensor, tile_size: int, overlap: int, rows=None,
+                            out: Optional[np.ndarray] = None) -> np.ndarray:
     """Warper.warp for a HOST image and a device-resident flow: the image goes up, is warped and comes back one
     tile row at a time on three streams, so the H2D and D2H transfers overlap (PCIe is full duplex) instead of
-    running back to back.  Same kernel, same rows, same result as warp_tiles."""
+    running back to back.  Same kernel, same rows, same result as warp_tiles.
+    rows = (r0, r1), a multiple-of-tile_size aligned band: only these output rows are produced (one rank of several);
+    out = host array to fill (page-locked or registered for asynchronous copies), default a fresh page-locked one."""
     a = np.ascontiguousarray(image)
     if a.dtype not in (np.uint8, np.uint16):
         raise TypeError(f"unsupported image dtype {a.dtype}; expected uint8 or uint16")
     h, w = a.shape
     T, ov = int(tile_size), int(overlap)
+    r0, r1 = (0, h) if rows is None else (int(rows[0]), int(rows[1]))
     dev = flow.device
     src = torch.from_numpy(a)
     img_d = torch.empty((h, w), dtype=src.dtype, device=dev)
     out_d = torch.empty_like(img_d)
-    out_h = torch.empty((h, w), dtype=src.dtype, pin_memory=True)
+    out_h = torch.empty((h, w), dtype=src.dtype, pin_memory=True) if out is None else torch.from_numpy(out)
+    if r1 <= r0:
+        return out_h.numpy()
     cur = torch.cuda.current_stream()
     up, comp, down = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
     for s in (up, comp, down):
         s.wait_stream(cur)          # the flow (and the allocations) were produced on the current stream
-    uploaded = 0
-    for y0 in range(0, h, T):
-        y1 = min(y0 + T, h)
+    uploaded = max(r0 - ov, 0)
+    if rows is not None:
+        pin_on_reuse(a, src[uploaded:min(r1 + ov, h)])
+    for y0 in range(r0, r1, T):
+        y1 = min(y0 + T, r1)
         need = min(y1 + ov, h)      # a tile row reads image rows [y0 - ov, y1 + ov)
         if need > uploaded:
             with torch.cuda.stream(up):

@@ -256,18 +256,30 @@ class Comm:
             for e, ok in zip(pool, free.tolist()):
                 if ok:
                     return self._hand_out(e)
-        name = [None]
+        # rank 0 creates an anonymous memory file (memfd: RAM-backed like /dev/shm but not limited by the size of that
+        # mount) and the other ranks open it through /proc; without memfd_create a file in /dev/shm (or the temp dir) does
+        nbytes = max(int(np.prod(shape)) * dtype.itemsize, 1)
+        name, fd = [None], None
         if self.rank == 0:
-            nbytes = int(np.prod(shape)) * dtype.itemsize
-            root = "/dev/shm" if os.path.isdir("/dev/shm") and _free_bytes("/dev/shm") > nbytes + (1 << 30) else tempfile.gettempdir()
             seq = self.__dict__["_shared_seq"] = self.__dict__.get("_shared_seq", 0) + 1
-            name[0] = os.path.join(root, f"microaligner_b200_{os.getpid()}_{seq}.shared")
-            np.memmap(name[0], dtype=dtype, mode="w+", shape=shape).flush()
+            try:
+                fd = os.memfd_create(f"microaligner_b200_{seq}")
+                os.ftruncate(fd, nbytes)
+                name[0] = f"/proc/{os.getpid()}/fd/{fd}"
+            except (AttributeError, OSError):
+                fd = None
+                root = "/dev/shm" if os.path.isdir("/dev/shm") and _free_bytes("/dev/shm") > nbytes + (1 << 30) else tempfile.gettempdir()
+                name[0] = os.path.join(root, f"microaligner_b200_{os.getpid()}_{seq}.shared")
+                with open(name[0], "wb") as f:
+                    f.truncate(nbytes)
         dist.broadcast_object_list(name, src=self._global[0], group=self.group)
         mm = np.memmap(name[0], dtype=dtype, mode="r+", shape=shape)
         self.barrier()
-        if self.rank == 0:
-            os.unlink(name[0])          # the mappings keep the pages alive
+        if self.rank == 0:          # the mappings keep the pages alive
+            if fd is not None:
+                os.close(fd)
+            else:
+                os.unlink(name[0])
         entry = {"mm": mm, "ref": None}
         pool.append(entry)
         return self._hand_out(entry)

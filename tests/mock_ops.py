@@ -147,6 +147,19 @@ def warp_tiles_rows(img, flow, tile_size, overlap, rows, out):
     return out
 
 
+def warp_tiles_host_streamed(image, flow, tile_size, overlap, rows=None, out=None):
+    """Only rows [rows[0] - overlap, rows[1] + overlap) of the host image are uploaded; only rows [rows) come back."""
+    h = image.shape[0]
+    r0, r1 = (0, h) if rows is None else (int(rows[0]), int(rows[1]))
+    res = np.empty_like(image) if out is None else out
+    if r1 > r0:
+        dev = to_device_rows(image, (max(r0 - int(overlap), 0), min(r1 + int(overlap), h)))
+        got = torch.from_numpy(_POISON.integers(0, 200, image.shape).astype(image.dtype))
+        warp_tiles_rows(dev, flow, tile_size, overlap, (r0, r1), got)
+        res[r0:r1] = got.numpy()[r0:r1]
+    return res
+
+
 def warp_tiles(img, flow, tile_size, overlap, out=None):
     out = torch.empty_like(img) if out is None else out
     return warp_tiles_rows(img, flow, tile_size, overlap, (0, img.shape[0]), out)

@@ -130,10 +130,16 @@ def _worker_host(rank, world, port, case, tmp):
         ref, mov = synth_pair(shape[0], shape[1], 3, dtype, amp=2.0, period=160.0)
         eng = engine.Engine(kw["tile_size"], kw["overlap"], kw["num_pyr_lvl"], kw["num_iterations"], kw["use_full_res_img"],
                             kw["use_dog"], comm=parallel.get(), log=lambda *a: None)
+        eng.group_tiles = 1             # one tile row per group: the speculative streaming of the last level is exercised
+        sinks, real = [], mock_ops.HostSink
+        mock_ops.HostSink = lambda host: sinks.append(real(host)) or sinks[-1]
         for rep in range(2):            # the second round reuses the node-shared result blocks of the first
+            del sinks[:]
             flow, flow_dev = eng.register_host(ref, mov)
+            flow_pushes = list(sinks[0].log)
             img = eng.warp_host(mov, flow_dev)
-            np.savez(os.path.join(tmp, f"r{rank}_{rep}.npz"), flow=flow, img=img, need=np.array(eng.full_input_rows(ref.shape)))
+            np.savez(os.path.join(tmp, f"r{rank}_{rep}.npz"), flow=flow, img=img, need=np.array(eng.full_input_rows(ref.shape)),
+                     pushes=np.array(flow_pushes))
             del flow, img
     finally:
         dist.destroy_process_group()
@@ -156,6 +162,11 @@ def test_host_io_on_several_ranks(tmp_path, case, world):
             assert np.array_equal(got["img"], want_img), f"rank {r} round {rep}: warped image differs"
         if case == "tiled levels, dog" and world == 3:       # every level sharded: a real share, not the whole image
             assert got["need"][1] - got["need"][0] < shape[0]
+        if case == "tiled levels, dog" and world == 2:       # 3 whole tile rows per rank: some are merged and sent early
+            pushes = [tuple(p) for p in got["pushes"]]
+            assert len(pushes) >= 2 and len(set(pushes)) == len(pushes), pushes
+            rows = sorted(pushes)
+            assert all(a[1] == b[0] for a, b in zip(rows, rows[1:])), pushes       # this rank's band exactly once
 
 
 STREAM_CASE = ((640, 530), np.uint16, dict(tile_size=100, overlap=16, num_pyr_lvl=1, num_iterations=1, use_full_res_img=True,
