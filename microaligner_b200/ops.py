@@ -114,47 +114,73 @@ def to_host_rows(t: torch.Tensor, rows) -> np.ndarray:
 
 
 # ---- caller-owned host memory: page-locking on reuse, asynchronous row uploads, streamed downloads -------------------
-_SEEN = {}       # (address, nbytes) -> times a pageable host range was uploaded
-_REGISTERED = {}  # (address, nbytes) -> True for ranges page-locked with cudaHostRegister
+_SEEN = {}        # (address, nbytes) -> times a pageable host range was uploaded
+_REGISTERED = []  # [start, end) byte intervals page-locked with cudaHostRegister (whole pages), kept sorted and disjoint
 PIN_MIN_BYTES = 32 << 20
+_PAGE = 4096
 
 
 def _clear_cuda_error():
+    """cudaHostRegister failures are not sticky, but they stay behind as the runtime's 'last error' and torch would report
+    them at its next launch check; cudaGetLastError of the runtime library torch itself loaded clears them."""
     import ctypes
-    for name in ("libcudart.so.12", "libcudart.so"):
+    try:
+        with open("/proc/self/maps") as f:
+            paths = sorted({ln.split()[-1] for ln in f if "libcudart" in ln})
+    except OSError:
+        paths = []
+    for path in paths + ["libcudart.so.12"]:
         try:
-            ctypes.CDLL(name).cudaGetLastError()
-            return
+            ctypes.CDLL(path).cudaGetLastError()
         except OSError:
             continue
 
 
-def _unregister(key):
-    if _REGISTERED.pop(key, None):
-        try:
-            torch.cuda.cudart().cudaHostUnregister(key[0])
-        except Exception:  # interpreter shutdown
-            pass
+def _unregister(intervals):
+    for iv in intervals:
+        if iv in _REGISTERED:
+            _REGISTERED.remove(iv)
+            try:
+                torch.cuda.cudart().cudaHostUnregister(iv[0])
+            except Exception:  # interpreter shutdown
+                pass
 
 
 def _register(arr: np.ndarray, view: torch.Tensor) -> bool:
-    key = (view.data_ptr(), view.numel() * view.element_size())
-    if key in _REGISTERED:
-        return True
-    if int(torch.cuda.cudart().cudaHostRegister(key[0], key[1], 0)) != 0:
-        # not page-lockable (e.g. a disk-backed mapping): copies from / to this range stay staged.  The sticky error
-        # code is cleared through the runtime library the process already has loaded.
-        _clear_cuda_error()
-        _SEEN[key] = -(1 << 30)        # do not try again
-        return False
-    _REGISTERED[key] = True
-    owner = arr
-    while isinstance(getattr(owner, "base", None), np.ndarray):
-        owner = owner.base
-    try:
-        weakref.finalize(owner, _unregister, key)
-    except TypeError:
-        pass
+    """Page-lock the whole pages under `view`; pages that already are (an overlapping range of the same array, e.g. the
+    rows register() uploaded and the rows warp() uploads) are skipped."""
+    lo = view.data_ptr() // _PAGE * _PAGE
+    hi = -(-(view.data_ptr() + view.numel() * view.element_size()) // _PAGE) * _PAGE
+    todo, cur = [], lo
+    for a, b in sorted(_REGISTERED):
+        if b <= cur or a >= hi:
+            continue
+        if a > cur:
+            todo.append((cur, a))
+        cur = max(cur, b)
+    if cur < hi:
+        todo.append((cur, hi))
+    done = []
+    for a, b in todo:
+        rc = int(torch.cuda.cudart().cudaHostRegister(a, b - a, 0))
+        if rc != 0:
+            # not page-lockable (e.g. a disk-backed mapping): copies from / to this range stay staged
+            _clear_cuda_error()
+            import sys
+            sys.stderr.write(f"microaligner_b200: cudaHostRegister({b - a} bytes) failed with error {rc}; copies stay staged\n")
+            _unregister(done)
+            _SEEN[(view.data_ptr(), view.numel() * view.element_size())] = -(1 << 30)        # do not try again
+            return False
+        _REGISTERED.append((a, b))
+        done.append((a, b))
+    if done:
+        owner = arr
+        while isinstance(getattr(owner, "base", None), np.ndarray):
+            owner = owner.base
+        try:
+            weakref.finalize(owner, _unregister, done)
+        except TypeError:
+            pass
     return True
 
 
