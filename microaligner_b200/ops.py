@@ -146,68 +146,60 @@ def _unregister(intervals):
                 pass
 
 
-def _register(arr: np.ndarray, view: torch.Tensor) -> bool:
-    """Page-lock the whole pages under `view`; pages that already are (an overlapping range of the same array, e.g. the
-    rows register() uploaded and the rows warp() uploads) are skipped."""
-    lo = view.data_ptr() // _PAGE * _PAGE
-    hi = -(-(view.data_ptr() + view.numel() * view.element_size()) // _PAGE) * _PAGE
-    todo, cur = [], lo
-    for a, b in sorted(_REGISTERED):
-        if b <= cur or a >= hi:
-            continue
-        if a > cur:
-            todo.append((cur, a))
-        cur = max(cur, b)
-    if cur < hi:
-        todo.append((cur, hi))
-    done = []
-    for a, b in todo:
-        rc = int(torch.cuda.cudart().cudaHostRegister(a, b - a, 0))
-        if rc != 0:
-            # not page-lockable (e.g. a disk-backed mapping): copies from / to this range stay staged
-            _clear_cuda_error()
-            import sys
-            sys.stderr.write(f"microaligner_b200: cudaHostRegister({b - a} bytes) failed with error {rc}; copies stay staged\n")
-            _unregister(done)
-            _SEEN[(view.data_ptr(), view.numel() * view.element_size())] = -(1 << 30)        # do not try again
-            return False
-        _REGISTERED.append((a, b))
-        done.append((a, b))
-    if done:
-        owner = arr
-        while isinstance(getattr(owner, "base", None), np.ndarray):
-            owner = owner.base
-        try:
-            weakref.finalize(owner, _unregister, done)
-        except TypeError:
-            pass
+def _root(arr: np.ndarray) -> np.ndarray:
+    while isinstance(getattr(arr, "base", None), np.ndarray):
+        arr = arr.base
+    return arr
+
+
+def _register(arr: np.ndarray) -> bool:
+    """Page-lock the WHOLE allocation `arr` is a view of (whole pages).  Never a part of it: CUDA rejects a copy whose
+    host range straddles the edge of a registered region, so a partially registered array would break copies of other
+    slices of it -- the caller's own included."""
+    root = _root(arr)
+    key = (root.ctypes.data, root.nbytes)
+    lo = key[0] // _PAGE * _PAGE
+    hi = -(-(key[0] + key[1]) // _PAGE) * _PAGE
+    if any(a <= lo and hi <= b for a, b in _REGISTERED):
+        return True
+    if _SEEN.get(key, 0) < 0 or any(a < hi and lo < b for a, b in _REGISTERED):
+        return False              # failed before, or overlaps another registration (two arrays sharing a page)
+    rc = int(torch.cuda.cudart().cudaHostRegister(lo, hi - lo, 0))
+    if rc != 0:
+        # not page-lockable (e.g. a disk-backed mapping): copies from / to this array stay staged
+        _clear_cuda_error()
+        import sys
+        sys.stderr.write(f"microaligner_b200: cudaHostRegister({hi - lo} bytes) failed with error {rc}; copies stay staged\n")
+        _SEEN[key] = -(1 << 30)        # do not try again
+        return False
+    _REGISTERED.append((lo, hi))
+    try:
+        weakref.finalize(root, _unregister, [(lo, hi)])
+    except TypeError:
+        pass
     return True
 
 
-def pin_on_reuse(arr: np.ndarray, view: torch.Tensor) -> bool:
-    """Page-lock the memory of `view` (a CPU tensor over rows of the caller's array `arr`) with cudaHostRegister the
-    SECOND time the same range is uploaded: a one-off upload of pageable memory is cheaper staged (registration costs
-    about as much as one staged copy), a repeated one -- the same reference image against many moving images, bench
-    loops -- then runs at DMA line rate.  The registration is dropped when `arr` is garbage collected."""
-    if view.numel() == 0 or view.is_pinned():
-        return True
-    nbytes = view.numel() * view.element_size()
-    key = (view.data_ptr(), nbytes)
-    if nbytes < PIN_MIN_BYTES:
+def pin_on_reuse(arr: np.ndarray) -> bool:
+    """Page-lock the caller's array with cudaHostRegister the SECOND time it is uploaded from: a one-off upload of
+    pageable memory is cheaper staged (registration costs about as much as one staged copy), a repeated one -- the same
+    reference image against many moving images, bench loops -- then runs at DMA line rate (55 vs 11 GB/s on the B200
+    hosts).  The registration is dropped when the array is garbage collected."""
+    root = _root(arr)
+    if root.nbytes < PIN_MIN_BYTES:
         return False
+    if arr.size and torch.from_numpy(arr.reshape(-1)[:1]).is_pinned():
+        return True
+    key = (root.ctypes.data, root.nbytes)
     n = _SEEN.get(key, 0) + 1
     _SEEN[key] = n
-    return _register(arr, view) if n >= 2 else False
+    return _register(arr) if n >= 2 else False
 
 
-def pin_rows(arr: np.ndarray, rows) -> bool:
-    """Page-lock rows [rows[0], rows[1]) of a host array now (idempotent): result blocks that are recycled from call to
-    call, e.g. the node-shared arrays of parallel.Comm.shared_host_empty."""
-    r0, r1 = int(rows[0]), int(rows[1])
-    if r1 <= r0:
-        return True
-    view = torch.from_numpy(arr)[r0:r1]
-    return True if view.is_pinned() else _register(arr, view)
+def pin_rows(arr: np.ndarray, rows=None) -> bool:
+    """Page-lock a host array now (idempotent; always the whole array, see _register): result blocks that are recycled
+    from call to call, e.g. the node-shared arrays of parallel.Comm.shared_host_empty."""
+    return _register(arr)
 
 
 def upload_rows_async(arr: np.ndarray, rows, device, stream: "torch.cuda.Stream"):
@@ -223,9 +215,8 @@ def upload_rows_async(arr: np.ndarray, rows, device, stream: "torch.cuda.Stream"
     stream.wait_stream(torch.cuda.current_stream())      # the allocation above is ordered on the current stream
     with torch.cuda.stream(stream):
         if r1 > r0:
-            view = src[r0:r1]
-            pin_on_reuse(a, view)
-            t[r0:r1].copy_(view, non_blocking=True)
+            pin_on_reuse(a)
+            t[r0:r1].copy_(src[r0:r1], non_blocking=True)
         ev.record(stream)
     return t, ev
 
@@ -368,7 +359,7 @@ def warp_tiles_host_streamed(image: np.ndarray, flow: torch.Tensor, tile_size: i
         s.wait_stream(cur)          # the flow (and the allocations) were produced on the current stream
     uploaded = max(r0 - ov, 0)
     if rows is not None:
-        pin_on_reuse(a, src[uploaded:min(r1 + ov, h)])
+        pin_on_reuse(a)
     for y0 in range(r0, r1, T):
         y1 = min(y0 + T, r1)
         need = min(y1 + ov, h)      # a tile row reads image rows [y0 - ov, y1 + ov)
