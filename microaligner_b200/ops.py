@@ -5,6 +5,7 @@ arithmetic happens in libmicroaligner_b200.so.  Images are 2-D uint8/uint16 tens
 carried as torch.uint16), flows are (H, W, 2) float32 tensors, all C-contiguous on one device."""
 import ctypes
 import os
+import sys
 import weakref
 from typing import Optional, Sequence
 
@@ -166,9 +167,17 @@ def _register(arr: np.ndarray) -> bool:
         return False              # failed before, or overlaps another registration (two arrays sharing a page)
     rc = int(torch.cuda.cudart().cudaHostRegister(lo, hi - lo, 0))
     if rc != 0:
+        # mapping host pages into the GPU's address space takes device memory (page tables), and torch's caching
+        # allocator may be sitting on all of it: give its cached blocks back and try once more
+        _clear_cuda_error()
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        rc = int(torch.cuda.cudart().cudaHostRegister(lo, hi - lo, 0))
+    if rc != 0:
         # not page-lockable (e.g. a disk-backed mapping): copies from / to this array stay staged
         _clear_cuda_error()
-        import sys
+        free, total = torch.cuda.mem_get_info()
+        sys.stderr.write(f"microaligner_b200: device memory free {free >> 20} MiB of {total >> 20} MiB\n")
         sys.stderr.write(f"microaligner_b200: cudaHostRegister({hi - lo} bytes) failed with error {rc}; copies stay staged\n")
         _SEEN[key] = -(1 << 30)        # do not try again
         return False

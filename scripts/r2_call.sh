@@ -1,24 +1,11 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
-echo "== NCCL parity, 2 ranks"
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 scripts/dist_check.py 5000 > gpurun_out/r2c5_dist2.log 2>&1; grep "identical" gpurun_out/r2c5_dist2.log; tail -3 gpurun_out/r2c5_dist2.log
-echo "== bench 2 GPUs, 20000 (quick)"
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --size 20000 > gpurun_out/r2c5_bench_2gpu_20000.json 2> gpurun_out/r2c5_bench_2gpu_20000.err; tail -c 400 gpurun_out/r2c5_bench_2gpu_20000.err
-python - <<'PY'
-import json
-for f in ['r2c5_bench_2gpu_20000']:
-    try:
-        d=json.loads(open(f'gpurun_out/{f}.json').read().strip().splitlines()[-1])
-        print(f,'value',round(d['value'],1),'ms',round(d['ms_per_step'],2),'e2e',round(d['e2e']['value'],1),round(d['e2e']['ms_per_step'],2), d['parity'], d['phases_ms']['max_over_ranks'])
-    except Exception as e: print(f,'ERR',e)
-PY
 echo "== bench 2 GPUs, default 50000"
-( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 2 > gpurun_out/r2c5_bench_2gpu_50000.json 2> gpurun_out/r2c5_bench_2gpu_50000.err ) 2>&1 | tail -3; tail -c 400 gpurun_out/r2c5_bench_2gpu_50000.err
+( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 2 > gpurun_out/r2c11_bench_2gpu_50000.json 2> gpurun_out/r2c11_bench_2gpu_50000.err ) 2>&1 | tail -3; grep "microaligner_b200:" gpurun_out/r2c11_bench_2gpu_50000.err | head
 python - <<'PY'
 import json
-for f in ['r2c5_bench_2gpu_50000']:
+for f in ['r2c11_bench_2gpu_50000']:
     try:
         d=json.loads(open(f'gpurun_out/{f}.json').read().strip().splitlines()[-1])
         print(f,'value',round(d['value'],1),'ms',round(d['ms_per_step'],2),'e2e',round(d['e2e']['value'],1),round(d['e2e']['ms_per_step'],2), d['parity'], d['phases_ms']['max_over_ranks'])
