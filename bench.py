@@ -235,12 +235,35 @@ class Bench:
         reg.gather_flow = False
         return reg, wrp
 
+    def probe_pin(self, tag, arr=None):
+        """MA_PIN_DEBUG=1: can this process page-lock 5 GB of fresh host memory (and `arr`) right now?"""
+        if not os.environ.get("MA_PIN_DEBUG"):
+            return
+        torch = self.torch
+        rt = torch.cuda.cudart()
+        a = np.ones(5 * 10 ** 9, np.uint8)
+        t = torch.from_numpy(a)
+        rc = int(rt.cudaHostRegister(t.data_ptr(), a.nbytes, 0))
+        if rc == 0:
+            rt.cudaHostUnregister(t.data_ptr())
+        msg = f"[pin probe rank {self.rank}] {tag}: anonymous 5 GB rc={rc}"
+        if arr is not None:
+            t2 = torch.from_numpy(arr)
+            rc2 = int(rt.cudaHostRegister(t2.data_ptr(), arr.nbytes, 0))
+            if rc2 == 0:
+                rt.cudaHostUnregister(t2.data_ptr())
+            msg += f", shared input {arr.nbytes / 1e9:.1f} GB rc={rc2}"
+        sys.stderr.write(msg + "\n")
+
     def measure(self, S, params, steps, warmup, profile=False, extras=False):
         """Device-resident and end-to-end timings of one workload; returns a dict."""
         torch = self.torch
         from microaligner_b200 import _lib
+        self.probe_pin("start")
         ref_h, mov_h = self.make_pair(S)
+        self.probe_pin("after make_pair", ref_h)
         ref_d, mov_d = torch.from_numpy(ref_h).to(self.dev), torch.from_numpy(mov_h).to(self.dev)   # replicated inputs
+        self.probe_pin("after device upload", ref_h)
         reg, wrp = self.registrator(params)
 
         def step_device():
@@ -259,6 +282,7 @@ class Bench:
         with quiet():
             for _ in range(warmup):
                 step_device()
+            self.probe_pin("after device warm-up", ref_h)
             if profile:
                 launches0 = _lib.lib.ma_launch_count()
                 _lib.lib.ma_profile_reset()
@@ -277,6 +301,7 @@ class Bench:
                 res["ms_fast"] = self.timed(step_device, steps)
                 reg.exact_arithmetic = True
                 res["phases"] = self.phases(step_device)
+            self.probe_pin("before the end-to-end leg", ref_h)
             # end to end through the numpy API
             for _ in range(max(3, warmup)):
                 step_host()

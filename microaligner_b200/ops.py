@@ -167,17 +167,22 @@ def _register(arr: np.ndarray) -> bool:
         return False              # failed before, or overlaps another registration (two arrays sharing a page)
     rc = int(torch.cuda.cudart().cudaHostRegister(lo, hi - lo, 0))
     if rc != 0:
-        # mapping host pages into the GPU's address space takes device memory (page tables), and torch's caching
-        # allocator may be sitting on all of it: give its cached blocks back and try once more
+        # cudaHostRegister has to get every page of the range resident at once, which fails with "OS call failed" when
+        # the kernel cannot produce them on the spot (hosts whose memory is hot-added / ballooned on demand, pages
+        # swapped out under pressure).  Ordinary page faults do wait for memory: touch every page, then try once more.
         _clear_cuda_error()
-        torch.cuda.synchronize()
-        torch.cuda.empty_cache()
+        try:
+            flat = root.reshape(-1).view(np.uint8) if root.flags.c_contiguous else None
+            if flat is not None:
+                step = 1 << 30
+                for o in range(0, flat.size, step):
+                    flat[o:o + step:_PAGE].max()
+        except (ValueError, AttributeError):
+            pass
         rc = int(torch.cuda.cudart().cudaHostRegister(lo, hi - lo, 0))
     if rc != 0:
         # not page-lockable (e.g. a disk-backed mapping): copies from / to this array stay staged
         _clear_cuda_error()
-        free, total = torch.cuda.mem_get_info()
-        sys.stderr.write(f"microaligner_b200: device memory free {free >> 20} MiB of {total >> 20} MiB\n")
         sys.stderr.write(f"microaligner_b200: cudaHostRegister({hi - lo} bytes) failed with error {rc}; copies stay staged\n")
         _SEEN[key] = -(1 << 30)        # do not try again
         return False
