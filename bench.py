@@ -187,16 +187,28 @@ class Bench:
         self.comm = parallel.get()
 
     # -- data: one copy of the pair in host memory that every rank can read (node-shared on several ranks) ----------
-    def make_pair(self, S):
+    def make_pair(self, S, params):
         from benchdata import synth_pair_large
+        from microaligner_b200 import ops
+        from microaligner_b200.engine import Engine
         torch = self.torch
         if self.world == 1:
             ref = torch.empty((S, S), dtype=torch.uint16, pin_memory=True).numpy()
             mov = torch.empty((S, S), dtype=torch.uint16, pin_memory=True).numpy()
             synth_pair_large(S, S, seed=0, out=(ref, mov))
             return ref, mov
+        # page-locked host inputs, as on one GPU: the pair lives once in node-shared memory and every rank locks the rows
+        # it is going to upload -- before they are filled, which is when these hosts let shared pages be locked
         ref = self.comm.shared_host_empty((S, S), np.uint16)
         mov = self.comm.shared_host_empty((S, S), np.uint16)
+        eng = Engine(params["tile_size"], params["overlap"], params["num_pyr_lvl"], params["num_iterations"],
+                     params["use_full_res_img"], params["use_dog"], comm=self.comm)
+        wb = eng.warp_band((S, S))
+        rows = eng.full_input_rows((S, S))
+        rows = (min(rows[0], max(wb[0] - eng.ov, 0)), max(rows[1], min(wb[1] + eng.ov, S))) if wb[1] > wb[0] else rows
+        for a in (ref, mov):
+            ops.pin_rows(a, rows)
+        self.comm.barrier()
         if self.rank == 0:
             synth_pair_large(S, S, seed=0, out=(ref, mov))
         self.comm.barrier()
@@ -235,35 +247,12 @@ class Bench:
         reg.gather_flow = False
         return reg, wrp
 
-    def probe_pin(self, tag, arr=None):
-        """MA_PIN_DEBUG=1: can this process page-lock 5 GB of fresh host memory (and `arr`) right now?"""
-        if not os.environ.get("MA_PIN_DEBUG"):
-            return
-        torch = self.torch
-        rt = torch.cuda.cudart()
-        a = np.ones(5 * 10 ** 9, np.uint8)
-        t = torch.from_numpy(a)
-        rc = int(rt.cudaHostRegister(t.data_ptr(), a.nbytes, 0))
-        if rc == 0:
-            rt.cudaHostUnregister(t.data_ptr())
-        msg = f"[pin probe rank {self.rank}] {tag}: anonymous 5 GB rc={rc}"
-        if arr is not None:
-            t2 = torch.from_numpy(arr)
-            rc2 = int(rt.cudaHostRegister(t2.data_ptr(), arr.nbytes, 0))
-            if rc2 == 0:
-                rt.cudaHostUnregister(t2.data_ptr())
-            msg += f", shared input {arr.nbytes / 1e9:.1f} GB rc={rc2}"
-        sys.stderr.write(msg + "\n")
-
     def measure(self, S, params, steps, warmup, profile=False, extras=False):
         """Device-resident and end-to-end timings of one workload; returns a dict."""
         torch = self.torch
         from microaligner_b200 import _lib
-        self.probe_pin("start")
-        ref_h, mov_h = self.make_pair(S)
-        self.probe_pin("after make_pair", ref_h)
+        ref_h, mov_h = self.make_pair(S, params)
         ref_d, mov_d = torch.from_numpy(ref_h).to(self.dev), torch.from_numpy(mov_h).to(self.dev)   # replicated inputs
-        self.probe_pin("after device upload", ref_h)
         reg, wrp = self.registrator(params)
 
         def step_device():
@@ -282,7 +271,6 @@ class Bench:
         with quiet():
             for _ in range(warmup):
                 step_device()
-            self.probe_pin("after device warm-up", ref_h)
             if profile:
                 launches0 = _lib.lib.ma_launch_count()
                 _lib.lib.ma_profile_reset()
@@ -301,7 +289,6 @@ class Bench:
                 res["ms_fast"] = self.timed(step_device, steps)
                 reg.exact_arithmetic = True
                 res["phases"] = self.phases(step_device)
-            self.probe_pin("before the end-to-end leg", ref_h)
             # end to end through the numpy API
             for _ in range(max(3, warmup)):
                 step_host()
@@ -370,8 +357,9 @@ class Bench:
             ok_f = ok_i = True
             for y0 in range(0, S, 2000):       # compare on the device, in bands
                 y1 = min(y0 + 2000, S)
-                ok_f &= bool(torch.equal(torch.from_numpy(np.ascontiguousarray(flow_h[y0:y1])).to(self.dev), flow_d[y0:y1]))
-                ok_i &= bool(torch.equal(torch.from_numpy(np.ascontiguousarray(img_h[y0:y1])).to(self.dev), img_d[y0:y1]))
+                # np.array: a private copy -- slices of the node-shared results may straddle the rows this rank page-locked
+                ok_f &= bool(torch.equal(torch.from_numpy(np.array(flow_h[y0:y1])).to(self.dev), flow_d[y0:y1]))
+                ok_i &= bool(torch.equal(torch.from_numpy(np.array(img_h[y0:y1])).to(self.dev), img_d[y0:y1]))
             out["numpy_api_equals_device_path"] = {"flow": ok_f, "image": ok_i}
         del flow_h, img_h
         if self.world > 1:

@@ -153,52 +153,47 @@ def _root(arr: np.ndarray) -> np.ndarray:
     return arr
 
 
-def _register(arr: np.ndarray) -> bool:
-    """Page-lock the WHOLE allocation `arr` is a view of (whole pages).  Never a part of it: CUDA rejects a copy whose
-    host range straddles the edge of a registered region, so a partially registered array would break copies of other
-    slices of it -- the caller's own included."""
-    root = _root(arr)
-    key = (root.ctypes.data, root.nbytes)
-    lo = key[0] // _PAGE * _PAGE
-    hi = -(-(key[0] + key[1]) // _PAGE) * _PAGE
-    if any(a <= lo and hi <= b for a, b in _REGISTERED):
-        return True
-    if _SEEN.get(key, 0) < 0 or any(a < hi and lo < b for a, b in _REGISTERED):
-        return False              # failed before, or overlaps another registration (two arrays sharing a page)
-    rc = int(torch.cuda.cudart().cudaHostRegister(lo, hi - lo, 0))
-    if rc != 0:
-        # cudaHostRegister has to get every page of the range resident at once, which fails with "OS call failed" when
-        # the kernel cannot produce them on the spot (hosts whose memory is hot-added / ballooned on demand, pages
-        # swapped out under pressure).  Ordinary page faults do wait for memory: touch every page, then try once more.
-        _clear_cuda_error()
+def _register(lo: int, hi: int, owner, touch=None) -> bool:
+    """cudaHostRegister of the whole pages under the byte range [lo, hi); pages that are registered already are skipped.
+    `owner`: the registration is dropped when this object is garbage collected."""
+    lo, hi = lo // _PAGE * _PAGE, -(-hi // _PAGE) * _PAGE
+    todo, cur = [], lo
+    for a, b in sorted(_REGISTERED):
+        if b <= cur or a >= hi:
+            continue
+        if a > cur:
+            todo.append((cur, a))
+        cur = max(cur, b)
+    if cur < hi:
+        todo.append((cur, hi))
+    done = []
+    for a, b in todo:
+        rc = int(torch.cuda.cudart().cudaHostRegister(a, b - a, 0))
+        if rc != 0:
+            # Not page-lockable: copies from / to this range stay staged (correct, ~5x slower).  Seen on hosts whose memory
+            # is hot-added on demand: cudaErrorOperatingSystem for ranges that are already populated, or larger than
+            # ~16 GB, while fresh (untouched) ranges of a few GB lock fine -- so lock result blocks when they are created.
+            _clear_cuda_error()
+            sys.stderr.write(f"microaligner_b200: cudaHostRegister({b - a} bytes) failed with error {rc}; copies stay staged\n")
+            _unregister(done)
+            return False
+        _REGISTERED.append((a, b))
+        done.append((a, b))
+    if done:
         try:
-            flat = root.reshape(-1).view(np.uint8) if root.flags.c_contiguous else None
-            if flat is not None:
-                step = 1 << 30
-                for o in range(0, flat.size, step):
-                    flat[o:o + step:_PAGE].max()
-        except (ValueError, AttributeError):
+            weakref.finalize(owner, _unregister, done)
+        except TypeError:
             pass
-        rc = int(torch.cuda.cudart().cudaHostRegister(lo, hi - lo, 0))
-    if rc != 0:
-        # not page-lockable (e.g. a disk-backed mapping): copies from / to this array stay staged
-        _clear_cuda_error()
-        sys.stderr.write(f"microaligner_b200: cudaHostRegister({hi - lo} bytes) failed with error {rc}; copies stay staged\n")
-        _SEEN[key] = -(1 << 30)        # do not try again
-        return False
-    _REGISTERED.append((lo, hi))
-    try:
-        weakref.finalize(root, _unregister, [(lo, hi)])
-    except TypeError:
-        pass
     return True
 
 
 def pin_on_reuse(arr: np.ndarray) -> bool:
-    """Page-lock the caller's array with cudaHostRegister the SECOND time it is uploaded from: a one-off upload of
+    """Page-lock the caller's WHOLE array with cudaHostRegister the SECOND time it is uploaded from: a one-off upload of
     pageable memory is cheaper staged (registration costs about as much as one staged copy), a repeated one -- the same
     reference image against many moving images, bench loops -- then runs at DMA line rate (55 vs 11 GB/s on the B200
-    hosts).  The registration is dropped when the array is garbage collected."""
+    hosts).  Whole arrays only: CUDA rejects a copy whose host range straddles the edge of a registered region, so a
+    partially locked array would break the caller's own copies of other slices of it.  The registration is dropped when
+    the array is garbage collected."""
     root = _root(arr)
     if root.nbytes < PIN_MIN_BYTES:
         return False
@@ -206,14 +201,29 @@ def pin_on_reuse(arr: np.ndarray) -> bool:
         return True
     key = (root.ctypes.data, root.nbytes)
     n = _SEEN.get(key, 0) + 1
+    if n < 0:
+        return False
     _SEEN[key] = n
-    return _register(arr) if n >= 2 else False
+    if n < 2:
+        return False
+    ok = _register(key[0], key[0] + key[1], root)
+    if not ok:
+        _SEEN[key] = -(1 << 30)        # do not try again
+    return ok
 
 
 def pin_rows(arr: np.ndarray, rows=None) -> bool:
-    """Page-lock a host array now (idempotent; always the whole array, see _register): result blocks that are recycled
-    from call to call, e.g. the node-shared arrays of parallel.Comm.shared_host_empty."""
-    return _register(arr)
+    """Page-lock rows [rows[0], rows[1]) of a C-contiguous host array now (idempotent; None = all rows): the blocks this
+    package owns and recycles from call to call -- each rank's rows of the node-shared results of
+    parallel.Comm.shared_host_empty, locked while they are still untouched -- and input arrays a caller prepares for
+    repeated use.  Copies issued by this package stay inside the locked rows; a caller who hands slices that straddle
+    their edge to CUDA directly must copy them first (np.array)."""
+    r0, r1 = (0, arr.shape[0]) if rows is None else (int(rows[0]), int(rows[1]))
+    if r1 <= r0 or not arr.flags.c_contiguous:
+        return r1 <= r0
+    row_bytes = arr.strides[0]
+    base = arr.ctypes.data
+    return _register(base + r0 * row_bytes, base + r1 * row_bytes, _root(arr))
 
 
 def upload_rows_async(arr: np.ndarray, rows, device, stream: "torch.cuda.Stream"):
