@@ -252,7 +252,10 @@ class Bench:
         torch = self.torch
         from microaligner_b200 import _lib
         ref_h, mov_h = self.make_pair(S, params)
-        ref_d, mov_d = torch.from_numpy(ref_h).to(self.dev), torch.from_numpy(mov_h).to(self.dev)   # replicated inputs
+        # replicated device inputs for the device-resident leg (uploaded from a private copy: on several ranks only part of
+        # the node-shared pair is page-locked by this rank, and CUDA rejects copies that straddle the edge of such a region)
+        ref_d = torch.from_numpy(ref_h if self.world == 1 else np.array(ref_h)).to(self.dev)
+        mov_d = torch.from_numpy(mov_h if self.world == 1 else np.array(mov_h)).to(self.dev)
         reg, wrp = self.registrator(params)
 
         def step_device():
