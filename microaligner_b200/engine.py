@@ -116,6 +116,7 @@ class Engine:
         # -- instead of computing a slice of every level and gathering the levels over NVLink.  Rows outside that range
         # stay uninitialised.  MA_LOCAL_PYRAMID=0 selects the gathering variant (A/B measurements).
         self.local_pyramid = os.environ.get("MA_LOCAL_PYRAMID", "1") not in ("", "0")
+        self.GATHER_BELOW = int(os.environ.get("MA_PYRAMID_GATHER_BELOW", Engine.GATHER_BELOW))   # see pyramid_plan()
         # rows of the final flow are handed to a host sink as soon as they are final; on one GPU the last level runs its
         # Farneback tile row by tile row and merges / downloads speculatively behind it (see register())
         self.stream_groups = True
@@ -194,13 +195,40 @@ class Engine:
                 req[k] = sup if req[k][1] <= req[k][0] else _union(req[k], sup)
         return req
 
-    def pyramid_local(self, arr: torch.Tensor, shapes, req: Sequence[Range]):
-        """pyramid() for one rank of several: level k holds valid data on rows req[k] only."""
+    GATHER_BELOW = 16384      # pyramid levels lower than this are completed on every rank (slices gathered over NVLink)
+
+    def pyramid_plan(self, shape):
+        """How one rank of several builds its pyramids.  Tiles have the same size at every level, so a band of tile rows
+        of a COARSE level maps to a large part of the full-resolution image (a third of it at the coarsest level of a
+        50 000^2 slide on 8 ranks): building every level band-locally would make each rank read and reduce that much.
+        Instead the first level lower than GATHER_BELOW rows is computed in equal slices and gathered (a few hundred MB
+        over NVLink), the coarser ones are reduced from it, replicated, and only the large levels above it are band-local.
+        Returns (shapes fine -> coarse, index of the gathered level or None, rows to compute per level, its slices)."""
+        shapes = self.level_shapes(tuple(shape))
+        gen = [LevelLayout(h, w, self.T, self.ov, self.comm) for h, w in shapes]
+        g = next((k for k, (h, _) in enumerate(shapes) if h < self.GATHER_BELOW), None)
+        top = len(shapes) if g is None else g + 1                      # levels [0, top) are computed by rows
+        need = [L.input_rows(self.use_dog) for L in gen[:top]]
+        slices = None
+        if g is not None:
+            slices = parallel.split_even(shapes[g][0], self.comm.world)
+            need[g] = slices[self.comm.rank]                           # the gather completes the level anyway
+        req = self.pyramid_requirements(need, [h for h, _ in shapes[:top]]) if need else []
+        return shapes, g, req, slices
+
+    def pyramid_local(self, arr: torch.Tensor, plan):
+        """pyramid() for one rank of several (see pyramid_plan): band-local levels hold valid data on their rows only."""
+        shapes, g, req, slices = plan
         pyr, cur = [], arr
-        for (h, w), rows in zip(shapes, req):
-            nxt = torch.empty((h, w), dtype=arr.dtype, device=arr.device)
-            if rows[1] > rows[0]:
-                ops.pyr_down_rows(cur, rows, nxt)
+        for k, (h, w) in enumerate(shapes):
+            if g is not None and k > g:
+                nxt = ops.pyr_down(cur)                                # small level, replicated
+            else:
+                nxt = torch.empty((h, w), dtype=arr.dtype, device=arr.device)
+                if req[k][1] > req[k][0]:
+                    ops.pyr_down_rows(cur, req[k], nxt)
+                if k == g:
+                    self.comm.gather_rows(nxt, slices)
             pyr.append(nxt)
             cur = nxt
         pyr.reverse()
@@ -266,15 +294,14 @@ class Engine:
         full = LevelLayout(ref.shape[0], ref.shape[1], T, ov, comm)
         with self.phase("pyramid"):
             if self.local_pyramid and comm.world > 1:
-                shapes = self.level_shapes(tuple(ref.shape))
-                gen = [LevelLayout(h, w, T, ov, comm) for h, w in shapes]          # fine -> coarse
-                req = self.pyramid_requirements([L.input_rows(self.use_dog) for L in gen], [h for h, _ in shapes])
+                plan = self.pyramid_plan(tuple(ref.shape))
+                shapes = plan[0]
                 if self.num_pyr_lvl < 0 or (not shapes and not self.full_res):
                     self.pyramid(ref)                                               # raises the reference's ValueErrors
                 ops.wait_upload(ready[0])
-                ref_pyr = self.pyramid_local(ref, shapes, req)
+                ref_pyr = self.pyramid_local(ref, plan)
                 ops.wait_upload(ready[1])
-                mov_pyr = self.pyramid_local(mov, shapes, req)
+                mov_pyr = self.pyramid_local(mov, plan)
                 factors = [2 ** (k + 1) for k in range(len(shapes))][::-1] + ([1] if self.full_res else [])
             else:
                 ops.wait_upload(ready[0])
@@ -503,11 +530,10 @@ class Engine:
         full = LevelLayout(shape[0], shape[1], self.T, self.ov, self.comm)
         if self.comm.world == 1 or not self.local_pyramid:
             return (0, full.h)
-        shapes = self.level_shapes(tuple(shape))
+        shapes, _, req, _ = self.pyramid_plan(tuple(shape))
         need = None
         if shapes:
-            gen = [LevelLayout(h, w, self.T, self.ov, self.comm) for h, w in shapes]
-            a, b = self.pyramid_requirements([L.input_rows(self.use_dog) for L in gen], [h for h, _ in shapes])[0]
+            a, b = req[0]
             if b > a:
                 need = _clip(2 * a - 2, 2 * b + 2, full.h)
         if self.full_res:

@@ -65,8 +65,10 @@ def _run(ref, mov, kw, local_pyramid=False, corrected=False):
         engine.ops, engine.torch = saved      # the single-rank run happens inside the pytest process
 
 
-def _worker(rank, world, port, case, tmp, local_pyramid, corrected=False):
+def _worker(rank, world, port, case, tmp, local_pyramid, corrected=False, gather_below=None):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    if gather_below is not None:
+        os.environ["MA_PYRAMID_GATHER_BELOW"] = str(gather_below)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from microaligner_b200 import parallel
     parallel.init(dist.group.WORLD)
@@ -104,14 +106,17 @@ def test_sharded_engine_equals_single_rank(tmp_path, case, world, local_pyramid)
         assert np.array_equal(got["img"], want_img), f"rank {r}: warped image differs"
 
 
-@pytest.mark.parametrize("world,case,corrected", [(5, "mixed levels", False), (2, "tiled levels, dog", True)])
-def test_sharded_engine_corner_cases(tmp_path, world, case, corrected):
+@pytest.mark.parametrize("world,case,corrected,gather_below", [(5, "mixed levels", False, None), (2, "tiled levels, dog", True, None),
+                                                               (3, "mixed levels", False, 150), (2, "tiled levels, dog", False, 100)])
+def test_sharded_engine_corner_cases(tmp_path, world, case, corrected, gather_below):
     """More ranks than tile rows (some ranks own no band at some levels); the opt-in corrected flow composition, which
-    gathers the accumulated flow before composing."""
+    gathers the accumulated flow before composing; and the pyramid plans the small test images do not reach by themselves:
+    a band-local level above the gathered one (threshold 150: levels of 215 and 108 rows), no gathered level at all."""
     shape, dtype, kw = CASES[case]
     ref, mov = synth_pair(shape[0], shape[1], 3, dtype, amp=2.0, period=160.0)
     want_flow, want_img, want_dec = _run(ref, mov, kw, corrected=corrected)
-    mp.spawn(_worker, args=(world, _free_port(), case, str(tmp_path), False, corrected), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), case, str(tmp_path), gather_below is not None, corrected, gather_below),
+             nprocs=world, join=True)
     for r in range(world):
         got = np.load(tmp_path / f"r{r}.npz")
         assert list(got["dec"]) == want_dec

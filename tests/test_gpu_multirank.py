@@ -39,10 +39,12 @@ def _run(ref, mov, kw):
     return flow.cpu().numpy(), w.warp().cpu().numpy(), [d["better"] for d in reg.decisions]
 
 
-def _worker(rank, world, port, case_id, tmp, gathered_pyramid=False):
+def _worker(rank, world, port, case_id, tmp, pyramid_mode=None):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
-    if gathered_pyramid:
+    if pyramid_mode == "gathered":
         os.environ["MA_LOCAL_PYRAMID"] = "0"    # read by Engine.__init__: pyramid levels computed in slices and gathered
+    elif pyramid_mode is not None:
+        os.environ["MA_PYRAMID_GATHER_BELOW"] = str(pyramid_mode)   # Engine.pyramid_plan: which level is gathered
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from microaligner_b200 import parallel
     parallel.init(dist.group.WORLD)
@@ -79,19 +81,21 @@ def test_sharded_equals_single(cuda, tmp_path, case_id, world):
 
 @pytest.mark.timeout(600)
 @pytest.mark.parametrize("world", [2, 3])
-def test_sharded_gathered_pyramid_equals_single(cuda, tmp_path, world):
-    """The band-local pyramid is the default (LOCAL_CASE has every level tiled, so it really leaves rows uncomputed);
-    MA_LOCAL_PYRAMID=0 selects the variant that computes every level in slices and gathers it."""
+def test_sharded_pyramid_plans_equal_single(cuda, tmp_path, world):
+    """Every way of building the pyramids on several ranks (Engine.pyramid_plan; LOCAL_CASE has every level tiled, so
+    band-local levels really leave rows uncomputed): the default plan (first level gathered, here), a band-local level
+    above the gathered one (threshold 400: levels of 650 and 325 rows), all levels band-local (threshold 1), and
+    MA_LOCAL_PYRAMID=0, which computes every level in slices and gathers it."""
     shape, dtype, kw = LOCAL_CASE
     ref, mov = synth_pair(shape[0], shape[1], 7, dtype)
     want_flow, want_img, want_dec = _run(ref, mov, kw)
-    for gathered in (False, True):
-        mp.spawn(_worker, args=(world, _free_port(), -1, str(tmp_path), gathered), nprocs=world, join=True)
+    for mode in (None, 400, 1, "gathered"):
+        mp.spawn(_worker, args=(world, _free_port(), -1, str(tmp_path), mode), nprocs=world, join=True)
         for r in range(world):
             got = np.load(tmp_path / f"r{r}.npz")
             assert list(got["dec"]) == want_dec
-            assert np.array_equal(got["flow"], want_flow), f"rank {r}: flow differs (gathered pyramid: {gathered})"
-            assert np.array_equal(got["img"], want_img), f"rank {r}: warped image differs (gathered pyramid: {gathered})"
+            assert np.array_equal(got["flow"], want_flow), f"rank {r}: flow differs (pyramid mode {mode})"
+            assert np.array_equal(got["img"], want_img), f"rank {r}: warped image differs (pyramid mode {mode})"
 
 
 def _worker_host(rank, world, port, tmp):

@@ -82,3 +82,24 @@ def test_local_pyramid_requirements(shape, T, ov, world, use_dog):
             if k + 1 < len(gen) and req[k + 1][1] > req[k + 1][0]:
                 ca, cb = req[k + 1]
                 assert a <= max(2 * ca - 2, 0) and b >= min(2 * cb + 2, L.h)
+
+
+@pytest.mark.parametrize("shape,world,frac", [((50000, 50000), 8, 0.18), ((50000, 50000), 2, 0.55), ((20000, 20000), 4, 0.31)])
+def test_pyramid_plan_keeps_the_upload_share_small(shape, world, frac):
+    """Hybrid pyramid (Engine.pyramid_plan): large levels band-local, the first level lower than GATHER_BELOW rows
+    gathered, coarser ones replicated -- so a rank reads about 1/world of the full-resolution images, not the third
+    that the coarse levels' tile rows would map to."""
+    from microaligner_b200.engine import Engine
+    for rank in range(world):
+        eng = Engine(1000, 100, 4, 3, True, False, comm=FakeComm(rank, world))
+        eng.local_pyramid = True
+        shapes, g, req, slices = eng.pyramid_plan(shape)
+        assert g is not None and shapes[g][0] < Engine.GATHER_BELOW and (g == 0 or shapes[g - 1][0] >= Engine.GATHER_BELOW)
+        assert len(req) == g + 1 and req[g] == slices[rank]
+        for k in range(g):       # band-local levels: own reads + support of the next level's rows
+            L = LevelLayout(shapes[k][0], shapes[k][1], 1000, 100, FakeComm(rank, world))
+            na, nb = L.input_rows(False)
+            assert req[k][0] <= na and req[k][1] >= nb
+            assert req[k][0] <= max(2 * req[k + 1][0] - 2, 0) and req[k][1] >= min(2 * req[k + 1][1] + 2, L.h)
+        r0, r1 = eng.full_input_rows(shape)
+        assert (r1 - r0) <= frac * shape[0], (rank, r0, r1)
