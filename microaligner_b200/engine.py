@@ -25,6 +25,14 @@ from . import ops, parallel
 Range = Tuple[int, int]
 
 
+def _nvtx():
+    """torch's NVTX binding (None when this build of torch has none)."""
+    try:
+        return torch.cuda.nvtx if torch.cuda.is_available() else None
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def _clip(a: int, b: int, h: int) -> Range:
     a = min(max(a, 0), h)
     return (a, min(max(b, a), h))
@@ -120,6 +128,7 @@ class Engine:
         # rows of the final flow are handed to a host sink as soon as they are final; on one GPU the last level runs its
         # Farneback tile row by tile row and merges / downloads speculatively behind it (see register())
         self.stream_groups = True
+        self.gather_pieces = 4       # pieces in which a sharded warp() sends its band to the other ranks
         self.group_tiles = 40        # tiles per Farneback launch of that streamed last level (enough CTAs to fill 148 SMs)
         self.flow_layout = None
 
@@ -127,20 +136,29 @@ class Engine:
         if self.comm.rank == 0:
             (self._log or print)(*a)
 
-    # optional phase tracing (Engine.trace = True): device-synchronised wall time per phase, summed in Engine.times
+    # Every phase of register() / warp() is an NVTX range (visible in Nsight Systems / ncu --nvtx), nested in one range
+    # per pyramid level.  Optional phase timing (Engine.trace = True): device-synchronised wall time per phase, summed
+    # in Engine.times -- bench.py prints it as `phases_ms`.
     trace = False
     times = defaultdict(float)
 
     @contextlib.contextmanager
     def phase(self, name):
-        if not Engine.trace:
+        nvtx = _nvtx()
+        if nvtx is not None:
+            nvtx.range_push("ma:" + name)
+        try:
+            if not Engine.trace:
+                yield
+                return
+            torch.cuda.synchronize()
+            t = time.perf_counter()
             yield
-            return
-        torch.cuda.synchronize()
-        t = time.perf_counter()
-        yield
-        torch.cuda.synchronize()
-        Engine.times[name] += time.perf_counter() - t
+            torch.cuda.synchronize()
+            Engine.times[name] += time.perf_counter() - t
+        finally:
+            if nvtx is not None:
+                nvtx.range_pop()
 
     # ------------------------------------------------------------------ building blocks
     def pyramid(self, arr: torch.Tensor):
@@ -315,6 +333,11 @@ class Engine:
 
         for lvl, factor in enumerate(factors):
             self.log("Pyramid factor", factor)
+            nvtx = _nvtx()
+            if nvtx is not None:
+                if lvl > 0:
+                    nvtx.range_pop()
+                nvtx.range_push(f"ma:level factor {factor}")
             L = layouts[lvl]
             B = L.band
             halo = ov + (20 if self.use_dog else 0)
@@ -457,6 +480,8 @@ class Engine:
             tail.__exit__(None, None, None)
             del this_flow
 
+        if _nvtx() is not None and factors:
+            _nvtx().range_pop()
         if m_flow is None:
             # no pyramid level at all: the reference fails on its unbound local (optflow_registrator.py:173)
             raise UnboundLocalError("cannot access local variable 'm_flow' where it is not associated with a value")
@@ -499,11 +524,18 @@ class Engine:
             tr = self.comm.tile_row_bands(L.ny)
             bands = [_clip(a * self.T, b * self.T, L.h) for a, b in tr]
             out = torch.empty_like(img)
-            with self.phase("warp"):
-                ops.warp_tiles_rows(img, flow, self.T, self.ov, bands[self.comm.rank], out)
-            if gather:
-                with self.phase("gather image"):
-                    self.comm.gather_rows(out, bands)
+            # the band is warped in a few pieces and every finished piece starts travelling while the next one is computed
+            pieces = self.gather_pieces if gather else 1
+            pending = []
+            for k in range(pieces):
+                sub = [(a + (b - a) * k // pieces, a + (b - a) * (k + 1) // pieces) for a, b in bands]
+                with self.phase("warp"):
+                    ops.warp_tiles_rows(img, flow, self.T, self.ov, sub[self.comm.rank], out)
+                if gather:
+                    pending.append(self.comm.gather_rows(out, sub, wait=False))
+            with self.phase("gather image"):
+                for p in pending:
+                    p.wait()
             return out
         return ops.warp_tiles(img, flow, self.T, self.ov)
 

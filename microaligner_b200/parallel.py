@@ -123,6 +123,20 @@ def chunk_range_of_band(band: Range, w: int, chunk: int, n: int) -> Range:
     return (c0, max(c0, c1))
 
 
+class _Done:
+    def wait(self):
+        pass
+
+
+class _Pending:
+    def __init__(self, reqs):
+        self.reqs = reqs
+
+    def wait(self):
+        for r in self.reqs:
+            r.wait()
+
+
 class Comm:
     def __init__(self, group=None):
         self.group = group
@@ -134,21 +148,27 @@ class Comm:
 
     # -- layout ---------------------------------------------------------------------------------
     def tile_row_bands(self, ny: int) -> List[Range]:
-        return split_even(ny, self.world)
+        """Tile rows per rank for the row-wise stages: boundaries at round(r * ny / world), i.e. as close as whole tile
+        rows get to the equal shares of TILES the Farneback stage works on (LevelLayout.fb_tiles) -- what has to move
+        between the two partitions after every Farneback call is at most half a tile row per boundary."""
+        cuts = [(r * ny + self.world // 2) // self.world for r in range(self.world + 1)]
+        return [(cuts[r], cuts[r + 1]) for r in range(self.world)]
 
     # -- data movement --------------------------------------------------------------------------
     def _wire(self, t: torch.Tensor) -> torch.Tensor:
         # NCCL (torch) has no 16-bit integer type: uint16 images travel as bytes, row slicing is unaffected
         return t.view(torch.uint8) if t.dtype == torch.uint16 else t
 
-    def exchange_rows(self, t: torch.Tensor, owned: Sequence[Range], need: Sequence[Range]):
-        """Make rows need[rank] of `t` valid on this rank, given that rank q holds rows owned[q]."""
+    def exchange_rows(self, t: torch.Tensor, owned: Sequence[Range], need: Sequence[Range], wait: bool = True):
+        """Make rows need[rank] of `t` valid on this rank, given that rank q holds rows owned[q].
+        wait=False returns a handle whose .wait() completes the exchange: the transfers run on the communication stream
+        while the caller keeps launching kernels (that must not touch the rows in flight)."""
         if self.world == 1:
-            return t
+            return t if wait else _Done()
         plan = transfer_plan(owned, need)
         mine = [p for p in plan if self.rank in (p[0], p[1])]
         if not mine:
-            return t
+            return t if wait else _Done()
         tw = self._wire(t)
         stage_cpu = self.backend == "gloo" and t.is_cuda
         ops, recvs = [], []
@@ -162,11 +182,14 @@ class Comm:
                 ops.append(dist.P2POp(dist.irecv, buf, self._global[src], group=self.group))
                 if stage_cpu:
                     recvs.append((view, buf))
-        for req in dist.batch_isend_irecv(ops):
+        reqs = dist.batch_isend_irecv(ops)
+        if not wait and not recvs:
+            return _Pending(reqs)
+        for req in reqs:
             req.wait()
         for view, buf in recvs:
             view.copy_(buf)
-        return t
+        return t if wait else _Done()
 
     def exchange_rects(self, t: torch.Tensor, have: Sequence[Sequence[Rect]], need_rows: Sequence[Range]):
         """Rank q holds the rectangles have[q] of `t` (rows x columns); make rows need_rows[rank] valid here."""
@@ -196,12 +219,12 @@ class Comm:
             view.copy_(buf)
         return t
 
-    def gather_rows(self, t: torch.Tensor, owned: Sequence[Range]):
+    def gather_rows(self, t: torch.Tensor, owned: Sequence[Range], wait: bool = True):
         """Every rank ends up with all rows of `t` (rank q contributes rows owned[q])."""
         if self.world == 1:
-            return t
+            return t if wait else _Done()
         full = (0, t.shape[0])
-        return self.exchange_rows(t, owned, [full] * self.world)
+        return self.exchange_rows(t, owned, [full] * self.world, wait=wait)
 
     def allreduce_minmax(self, mm: torch.Tensor):
         """mm = (..., 2) float32 [min, max] pairs (device); reduced in place over the group, one collective."""
