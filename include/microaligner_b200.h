@@ -156,6 +156,12 @@ int ma_nmi_chunks(const uint8_t* a, const uint8_t* b, size_t n, size_t chunk,
 int ma_nmi_chunk_range(const uint8_t* a, const uint8_t* b, size_t n, size_t chunk, size_t chunk_begin, size_t chunk_end,
                        double* scores_out, void* workspace, void* stream);
 
+/* the gate's two comparisons in one launch (check_if_higher_similarity, similarity_scoring.py:61-68: mi_tiled(ref, warped)
+ * and mi_tiled(ref, unwarped)): scores0[c] = NMI(a, b0), scores1[c] = NMI(a, b1) for chunks [chunk_begin, chunk_end).
+ * b1 / scores1 may be NULL (one comparison). */
+int ma_nmi_chunk_range2(const uint8_t* a, const uint8_t* b0, const uint8_t* b1, size_t n, size_t chunk, size_t chunk_begin,
+                        size_t chunk_end, double* scores0, double* scores1, void* stream);
+
 /* ---- pipeline input prep (shared_modules/utils.py:75-95): z max-projection of n_pages images
  * followed by cv.normalize(.., 0, 255, NORM_MINMAX, CV_8U). pages_host is a HOST array of n_pages
  * device pointers (same pitch/dtype). workspace: ma_zmip_workspace_bytes(h, w, dtype). */

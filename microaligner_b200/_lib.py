@@ -42,6 +42,7 @@ PROTOTYPES = {
     "ma_dog_band_workspace_bytes": (c_size_t, [c_int, c_int]),
     "ma_dog_quantize_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "ma_nmi_chunk_range": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_size_t, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "ma_nmi_chunk_range2": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_size_t, c_size_t, c_void_p, c_void_p, c_void_p]),
     "ma_compose_flows_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "ma_merge_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "ma_merge_flows_tiles": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),

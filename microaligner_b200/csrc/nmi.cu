@@ -47,8 +47,11 @@ constexpr int kNmiThreads = 256;
 constexpr int kNmiUnroll = 4;                      // 16-pixel vectors of each image in flight per thread
 
 __global__ void __cluster_dims__(kNmiCluster, 1, 1) __launch_bounds__(kNmiThreads)
-nmi_chunk_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, size_t n, size_t chunk, size_t chunk0,
-                 double* __restrict__ scores) {
+nmi_chunk_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b0, const uint8_t* __restrict__ b1, size_t n,
+                 size_t chunk, size_t chunk0, double* __restrict__ scores0, double* __restrict__ scores1) {
+    // blockIdx.y selects the image compared with `a`: the gate scores (a, b0) and (a, b1) in one launch
+    const uint8_t* __restrict__ b = blockIdx.y ? b1 : b0;
+    double* __restrict__ scores = blockIdx.y ? scores1 : scores0;
     extern __shared__ unsigned hist[];              // [kSlabRows][256]: rows rank*64 .. rank*64+63 of the joint histogram
     __shared__ unsigned pi[kSlabRows];              // row sums of my slab
     __shared__ unsigned pj_part[256];               // column sums of my slab
@@ -212,9 +215,11 @@ extern "C" size_t ma_nmi_workspace_bytes(size_t n, size_t chunk) {
     return 0;       // the joint histograms live in (distributed) shared memory; kept in the ABI for callers that size a scratch
 }
 
-extern "C" int ma_nmi_chunk_range(const uint8_t* a, const uint8_t* b, size_t n, size_t chunk, size_t chunk_begin, size_t chunk_end,
-                                  double* scores_out, void* workspace, void* stream) {
-    (void)workspace;
+extern "C" int ma_nmi_chunk_range2(const uint8_t* a, const uint8_t* b0, const uint8_t* b1, size_t n, size_t chunk,
+                                   size_t chunk_begin, size_t chunk_end, double* scores0, double* scores1, void* stream) {
+    const uint8_t* b = b0;
+    double* scores_out = scores0;
+    if (b1 && !scores1) return invalid("ma_nmi_chunks: bad argument");
     if (!a || !b || !scores_out || n == 0 || chunk == 0) return invalid("ma_nmi_chunks: bad argument");
     if (chunk > 0xffffffffull) return invalid("ma_nmi_chunks: chunk must fit 32-bit counters");
     cudaStream_t s = (cudaStream_t)stream;
@@ -231,11 +236,17 @@ extern "C" int ma_nmi_chunk_range(const uint8_t* a, const uint8_t* b, size_t n, 
     }
     for (size_t c0 = chunk_begin; c0 < chunk_end; c0 += 16384) {       // grid.x limit is far away; keep launches bounded
         const int g = (int)std::min<size_t>(16384, chunk_end - c0);
-        KernelScope ks(K_NMI_HIST, s, (double)std::min<size_t>(n - c0 * chunk, (size_t)g * chunk));
-        nmi_chunk_kernel<<<g * kNmiCluster, kNmiThreads, smem, s>>>(a, b, n, chunk, c0, scores_out);
+        KernelScope ks(K_NMI_HIST, s, (b1 ? 2.0 : 1.0) * (double)std::min<size_t>(n - c0 * chunk, (size_t)g * chunk));
+        nmi_chunk_kernel<<<dim3(g * kNmiCluster, b1 ? 2 : 1), kNmiThreads, smem, s>>>(a, b0, b1, n, chunk, c0, scores0, scores1);
     }
     MA_LAUNCH_CHECK("nmi_chunk_kernel");
     return MA_OK;
+}
+
+extern "C" int ma_nmi_chunk_range(const uint8_t* a, const uint8_t* b, size_t n, size_t chunk, size_t chunk_begin, size_t chunk_end,
+                                  double* scores_out, void* workspace, void* stream) {
+    (void)workspace;
+    return ma_nmi_chunk_range2(a, b, nullptr, n, chunk, chunk_begin, chunk_end, scores_out, nullptr, stream);
 }
 
 extern "C" int ma_nmi_chunks(const uint8_t* a, const uint8_t* b, size_t n, size_t chunk,

@@ -289,8 +289,11 @@ class Engine:
         nchunks = -(-n // chunk)
         scores = torch.zeros((len(bs), nchunks), dtype=torch.float64, device=a.device)
         cr = parallel.chunk_range_of_band(L.band, L.w, chunk, n) if L.sharded else (0, nchunks)
-        for i, b in enumerate(bs):
-            ops.nmi_chunk_range(a, b, chunk, cr, scores[i])
+        if len(bs) == 2:
+            ops.nmi_chunk_range2(a, bs[0], bs[1], chunk, cr, scores[0], scores[1])
+        else:
+            for i, b in enumerate(bs):
+                ops.nmi_chunk_range(a, b, chunk, cr, scores[i])
         if L.sharded:
             self.comm.allreduce_sum(scores)
         host = scores.cpu().numpy()

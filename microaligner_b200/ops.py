@@ -599,6 +599,12 @@ def dog_quantize_rows(diff, h, w, diff_minmax, rows, out):
     return out
 
 
+def nmi_chunk_range2(a, b0, b1, chunk, chunk_range, scores0, scores1):
+    """Both comparisons of the similarity gate in one launch: scores0 = NMI(a, b0), scores1 = NMI(a, b1) per chunk."""
+    check(lib.ma_nmi_chunk_range2(a.data_ptr(), b0.data_ptr(), b1.data_ptr(), a.numel(), int(chunk), int(chunk_range[0]),
+                                  int(chunk_range[1]), scores0.data_ptr(), scores1.data_ptr(), _stream()), "ma_nmi_chunk_range2")
+
+
 def nmi_chunk_range(a, b, chunk, chunk_range, scores):
     n = a.numel()
     check(lib.ma_nmi_chunk_range(a.data_ptr(), b.data_ptr(), n, int(chunk), int(chunk_range[0]), int(chunk_range[1]),

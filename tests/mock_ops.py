@@ -253,6 +253,11 @@ def dog_quantize_rows(diff, h, w, diff_minmax, rows, out):
     return out
 
 
+def nmi_chunk_range2(a, b0, b1, chunk, chunk_range, scores0, scores1):
+    nmi_chunk_range(a, b0, chunk, chunk_range, scores0)
+    nmi_chunk_range(a, b1, chunk, chunk_range, scores1)
+
+
 def nmi_chunk_range(a, b, chunk, chunk_range, scores):
     fa, fb_ = _np(a).ravel(), _np(b).ravel()
     for c in range(int(chunk_range[0]), int(chunk_range[1])):

@@ -142,6 +142,19 @@ def test_nmi(ops):
     assert ops.nmi_chunks(dev(z), dev(z), z.size).cpu().numpy()[0] == 1.0
     assert ops.nmi_chunks(dev(z), dev(b), z.size).cpu().numpy()[0] == 0.0
     assert ops.nmi_chunks(dev(a), dev(a), a.size).cpu().numpy()[0] == pytest.approx(1.0, rel=1e-12)
+    # both comparisons of the gate in one launch == two single launches, bit for bit; unaligned chunk starts; noise
+    import torch
+    rng = np.random.default_rng(0)
+    c = rng.integers(0, 256, a.shape).astype(np.uint8)
+    for chunk in (300 * 300, 150 * 150 + 7):
+        n = -(-a.size // chunk)
+        s0 = torch.zeros(n, dtype=torch.float64, device="cuda")
+        s1 = torch.zeros(n, dtype=torch.float64, device="cuda")
+        ops.nmi_chunk_range2(dev(a), dev(b), dev(c), chunk, (0, n), s0, s1)
+        assert torch.equal(s0, ops.nmi_chunks(dev(a), dev(b), chunk)) and torch.equal(s1, ops.nmi_chunks(dev(a), dev(c), chunk))
+        fc = c.ravel()
+        np.testing.assert_allclose(s1.cpu().numpy(), [cv_ops.nmi(fa[s:s + chunk], fc[s:s + chunk]) for s in range(0, fa.size, chunk)],
+                                   rtol=1e-12)
 
 
 def test_zmip(ops):
