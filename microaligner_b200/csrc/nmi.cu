@@ -6,22 +6,22 @@
 //
 // One thread-block CLUSTER of four CTAs per chunk (nmi_chunk_kernel).  The 256 x 256 joint histogram (256 KB as u32)
 // does not fit one SM's shared memory, so it is split into four 64-row slabs, one per CTA of the cluster (64 KB each).
-// Every CTA scans the whole chunk -- 16 pixels of `a` per thread from one 128-bit load -- and keeps the pixels whose
-// `a` value falls into its slab: a SIMD byte compare rejects vectors without such a pixel before `b` is even loaded
-// (DoG images are smooth, so three quarters of the vectors are skipped), equal consecutive (a, b) pairs are merged in
-// registers, and each run is one shared-memory atomic (four vectors of both images in flight per thread).  No global histogram, no L2 atomics, no memset, one launch per
-// call.  After the scan each CTA reduces its slab: row sums, its share of the column sums (exchanged through
-// distributed shared memory), and its part of
+// Every CTA scans the whole chunk -- 16 pixels of both images per thread from two 128-bit loads -- and keeps the pixels
+// whose `a` value falls into its slab; equal consecutive (a, b) pairs are merged in registers, and each run is one
+// shared-memory atomic.  No global histogram, no L2 atomics, no memset, one launch for both comparisons of the gate.
+// After the scan each CTA reduces its slab: row sums, its share of the column sums (exchanged through distributed
+// shared memory), and its part of
 //   MI = sum_{J>0} J/n (ln J - ln n) + J/n (-ln(a_i b_j) + 2 ln n),  H(a), H(b)
 // in f64; CTA 0 adds the four parts in rank order (deterministic) and writes NMI = MI / mean(H_a, H_b) with sklearn's
 // special cases (both labelings constant -> 1, MI == 0 -> 0).  One double per chunk leaves the kernel; the mean over
 // chunks and the `after > before` decision are taken by the host from two doubles.
 //
-// Measured on B200, 144 chunks of 10^6 px (profiles/r02_ab_variants.log, profiles/r02_nmi_cluster.log): histogram in an
-// L2-resident global scratch + separate entropy kernel 1.67 ms (warp-aggregated atomics) / 1.22 ms (run-length
-// merging) -- bound by the L2 atomic unit serialising the hot bins of smooth images; this kernel with every CTA
-// scanning a quarter of the chunk and adding to remote slabs (red.shared::cluster) 1.77 ms -- remote shared-memory
-// atomics are slow; scanning everything and adding locally 0.85 ms, before the skip test.
+// Measured on B200, 144 chunks of 10^6 px, ms per call (profiles/r02_ab_variants.log, profiles/r02_nmi_cluster.log):
+// histogram in an L2-resident global scratch + separate entropy kernel 1.67 (warp-aggregated atomics) / 1.22 (run-length
+// merging) -- bound by the L2 atomic unit serialising the hot bins of smooth images; this kernel with every CTA scanning
+// a quarter of the chunk and adding to REMOTE slabs (red.shared::cluster) 1.77 -- remote shared-memory atomics are slow;
+// scanning everything and adding locally 0.74.  The scan is latency-bound: 512 threads beat 256 (0.74 vs 1.04), more
+// loads in flight per thread or a SIMD test that skips vectors without a pixel of the slab do not pay (0.80 - 0.97).
 #include <atomic>
 #include <cooperative_groups.h>
 #include "common.cuh"
@@ -37,14 +37,14 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
     __syncthreads();
     double t = 0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
+    for (int i = 0; i < kNmiThreads / 32; ++i) t += sh[i];
     return t;
 }
 
 constexpr int kNmiCluster = 4;                     // CTAs per chunk
 constexpr int kSlabRows = 256 / kNmiCluster;       // rows of the joint histogram per CTA
-constexpr int kNmiThreads = 256;
-constexpr int kNmiUnroll = 4;                      // 16-pixel vectors of each image in flight per thread
+constexpr int kNmiThreads = 512;                   // 3 CTAs x 16 warps per SM: the scan is latency-bound, warps are what helps
+
 
 __global__ void __cluster_dims__(kNmiCluster, 1, 1) __launch_bounds__(kNmiThreads)
 nmi_chunk_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b0, const uint8_t* __restrict__ b1, size_t n,
@@ -86,45 +86,25 @@ nmi_chunk_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b0, 
         }
         const uint4* va = reinterpret_cast<const uint4*>(pa + head);
         const uint4* vb = reinterpret_cast<const uint4*>(pb + head);
-        const unsigned mine = rank * 0x01010101u;
-        // kNmiUnroll vectors of both images are in flight per thread before any of them is looked at: with one vector at a
-        // time the scan was bound by the latency of its two dependent loads (ncu: 29 % issue, 3 % DRAM)
-        for (size_t v0 = t; v0 < nvec; v0 += (size_t)kNmiUnroll * kNmiThreads) {
-            uint4 A[kNmiUnroll], B[kNmiUnroll];
+        for (size_t v = t; v < nvec; v += kNmiThreads) {
+            const uint4 A = __ldg(va + v), B = __ldg(vb + v);
+            const unsigned aw[4] = {A.x, A.y, A.z, A.w}, bw[4] = {B.x, B.y, B.z, B.w};
+            unsigned run_a = 0, run_b = 0, cnt = 0;
 #pragma unroll
-            for (int u = 0; u < kNmiUnroll; ++u) {
-                const size_t v = v0 + (size_t)u * kNmiThreads;
-                if (v < nvec) {
-                    A[u] = __ldg(va + v);
-                    B[u] = __ldg(vb + v);
+            for (int q = 0; q < 16; ++q) {
+                const int sh = 8 * (q & 3);
+                const unsigned av = (aw[q >> 2] >> sh) & 255u, bv = (bw[q >> 2] >> sh) & 255u;
+                const bool o = av / kSlabRows == rank;
+                if (o && cnt != 0 && av == run_a && bv == run_b) {
+                    ++cnt;
+                } else {
+                    if (cnt != 0) add(run_a, run_b, cnt);
+                    run_a = av;
+                    run_b = bv;
+                    cnt = o ? 1u : 0u;
                 }
             }
-#pragma unroll
-            for (int u = 0; u < kNmiUnroll; ++u) {
-                if (v0 + (size_t)u * kNmiThreads >= nvec) break;
-                const unsigned aw[4] = {A[u].x, A[u].y, A[u].z, A[u].w};
-                unsigned own[4];          // 0xff in every byte whose a value belongs to my slab (a >> 6 == rank)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) own[k] = __vcmpeq4((aw[k] >> 6) & 0x03030303u, mine);
-                if ((own[0] | own[1] | own[2] | own[3]) == 0) continue;          // nothing of mine in these 16 pixels
-                const unsigned bw[4] = {B[u].x, B[u].y, B[u].z, B[u].w};
-                unsigned run_a = 0, run_b = 0, cnt = 0;
-#pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    const int sh = 8 * (q & 3);
-                    const unsigned av = (aw[q >> 2] >> sh) & 255u, bv = (bw[q >> 2] >> sh) & 255u;
-                    const bool o = (own[q >> 2] >> sh) & 1u;
-                    if (o && cnt != 0 && av == run_a && bv == run_b) {
-                        ++cnt;
-                    } else {
-                        if (cnt != 0) add(run_a, run_b, cnt);
-                        run_a = av;
-                        run_b = bv;
-                        cnt = o ? 1u : 0u;
-                    }
-                }
-                if (cnt != 0) add(run_a, run_b, cnt);
-            }
+            if (cnt != 0) add(run_a, run_b, cnt);
         }
     }
     __syncthreads();                                // my slab is final

@@ -24,4 +24,16 @@ w.image, w.flow = mov, flow
 out = w.warp()
 pages = [ops.to_device(ref), ops.to_device(mov)]
 mip = ops.zmip_normalize_u8(pages)
+# paths the small run above does not reach: uint8 images (scalar-store warp path on the odd width), an odd-width flow,
+# untiled Farneback, full iteration windows, the affine resampler and the opt-in flow composition
+import torch  # noqa: E402
+r8, m8 = synth_pair(301, 333, 2, np.uint8)
+d8r, d8m = ops.to_device(r8), ops.to_device(m8)
+f8 = ops.farneback_tiles(d8m, d8r, 0, 0, 31, 2)
+f8b = ops.farneback_tiles(d8m, d8r, 100, 12, 11, 2, full_windows=True)
+w8 = ops.warp_tiles(d8m, f8, 100, 12)
+mg = ops.merge_flows_tiles(f8, f8b, 100, 12)
+cf = ops.compose_flows_rows(f8, f8b, (0, 301), torch.empty_like(f8))
+af = ops.warp_affine(d8m, np.linalg.pinv(np.array([[0.99, 0.02, 1.5], [-0.02, 0.99, -2.0], [0, 0, 1]])), (320, 350), 9, 8)
+torch.cuda.synchronize()
 print("sanitize run ok", float(np.abs(flow).max()), int(out.max()), int(mip.max()))
