@@ -30,6 +30,10 @@ namespace ma {
 
 namespace cg = cooperative_groups;
 
+constexpr int kNmiCluster = 4;                     // CTAs per chunk
+constexpr int kSlabRows = 256 / kNmiCluster;       // rows of the joint histogram per CTA
+constexpr int kNmiThreads = 512;                   // 3 CTAs x 16 warps per SM: the scan is latency-bound, warps are what helps
+
 __device__ __forceinline__ double block_sum(double v, double* sh) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -41,9 +45,6 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
     return t;
 }
 
-constexpr int kNmiCluster = 4;                     // CTAs per chunk
-constexpr int kSlabRows = 256 / kNmiCluster;       // rows of the joint histogram per CTA
-constexpr int kNmiThreads = 512;                   // 3 CTAs x 16 warps per SM: the scan is latency-bound, warps are what helps
 
 
 __global__ void __cluster_dims__(kNmiCluster, 1, 1) __launch_bounds__(kNmiThreads)
