@@ -30,6 +30,24 @@ from .pipeline_modules.metadata_handling import DatasetStruct, DatasetStructCrea
 from .pipeline_modules.ome_meta_processing import create_new_meta
 
 Shape2D = Tuple[int, int]
+TIMES: Dict[str, float] = {}      # MA_PIPELINE_TIMING=1: device-synchronised wall seconds per stage (scripts/bench_pipeline.py)
+
+
+class _stage:
+    def __init__(self, name):
+        self.name, self.on = name, bool(os.environ.get("MA_PIPELINE_TIMING"))
+
+    def __enter__(self):
+        if self.on:
+            import time
+            torch.cuda.synchronize()
+            self.t = time.perf_counter()
+
+    def __exit__(self, *a):
+        if self.on:
+            import time
+            torch.cuda.synchronize()
+            TIMES[self.name] = TIMES.get(self.name, 0.0) + time.perf_counter() - self.t
 
 
 def _say(*a):
@@ -171,7 +189,8 @@ def register_and_save_ofreg_imgs(dataset_struct: DatasetStruct, out_dir: Path, f
             img_memmap = create_memmap_for_saving(out_dir / filenames["per_cycle"].format(cyc=cyc), shape, img_dtype,
                                                   ome_meta_per_cyc[cyc])
         ref_ch_id = dataset_struct.ref_channel_ids[cyc]
-        mip = read_and_max_project_pages(reader, dataset_struct.img_paths[cyc][ref_ch_id], dataset_struct.tiff_pages[cyc][ref_ch_id])
+        with _stage("read + max-project"):
+            mip = read_and_max_project_pages(reader, dataset_struct.img_paths[cyc][ref_ch_id], dataset_struct.tiff_pages[cyc][ref_ch_id])
         # the independent pages of this cycle: (output channel index, z index, file, TIFF page)
         jobs = []
         for ch_id, ch in enumerate(dataset_struct.tiff_pages[cyc]):
@@ -185,15 +204,19 @@ def register_and_save_ofreg_imgs(dataset_struct: DatasetStruct, out_dir: Path, f
             _say("Skipping as it is a reference image")
             ref_img = mip
             _say(f"Saving Cycle {cyc} [{cyc_id + 1}/{ncycles}]")
-            save_pages(img_memmap, reader, jobs)
+            with _stage("save pages (first cycle)"):
+                save_pages(img_memmap, reader, jobs)
         else:
             ofreg.ref_img, ofreg.mov_img = ref_img, mip       # device tensors: the flow stays on the GPU
-            flow = ofreg.register()
+            with _stage("register"):
+                flow = ofreg.register()
             decisions[cyc] = ofreg.decisions
             warper.image, warper.flow = mip, flow
-            ref_img = warper.warp()                            # reference of the next cycle
+            with _stage("warp of the projection"):
+                ref_img = warper.warp()                        # reference of the next cycle
             _say(f"Saving Cycle {cyc} [{cyc_id + 1}/{ncycles}]")
-            warp_and_save_pages(img_memmap, reader, flow, jobs, tile_size, overlap)
+            with _stage("warp + save pages"):
+                warp_and_save_pages(img_memmap, reader, flow, jobs, tile_size, overlap)
             del flow
         img_memmap.flush()
         if not save_to_stack:
