@@ -70,6 +70,7 @@ class PageReader:
         self._files: Dict[str, tiffio.TiffFile] = {}
         self._ring: List[np.ndarray] = []
         self._n, self._next = n_buffers, 0
+        self.ring_size = n_buffers
 
     def _page(self, path, index) -> tiffio.TiffPage:
         key = os.fspath(path)
@@ -108,7 +109,13 @@ def create_memmap_for_saving(output_path: Path, img_shape, img_dtype, ome_meta: 
 
 def read_and_max_project_pages(reader: PageReader, img_paths: Dict[int, Path], tiff_pages: Dict[int, int]) -> torch.Tensor:
     """z max-projection + 8-bit min-max normalisation (shared_modules/utils.py:75-95) on the device."""
-    return ops.zmip_normalize_u8([ops.to_device(reader.read(img_paths[z], tiff_pages[z], pinned=False)) for z in img_paths])
+    pages = []
+    for z in img_paths:      # page-locked ring buffer -> asynchronous upload; the next page is read meanwhile
+        host = reader.read(img_paths[z], tiff_pages[z])
+        pages.append(torch.from_numpy(host).to("cuda", non_blocking=True))
+        if len(pages) >= reader.ring_size - 1:      # never overwrite a buffer whose upload may still be running
+            torch.cuda.current_stream().synchronize()
+    return ops.zmip_normalize_u8(pages)
 
 
 def _my_share(n_items: int) -> List[int]:
@@ -121,7 +128,7 @@ def save_pages(mm, reader: PageReader, jobs: List[Tuple[int, int, Path, int]]):
     """First cycle: pages pass through unchanged (__main__.py:305-317).  jobs = (channel index, z index, path, page)."""
     for k in _my_share(len(jobs)):
         ch_id, z_id, path, page = jobs[k]
-        mm[0, ch_id, z_id, :, :] = reader.read(path, page, pinned=False)
+        tiffio.write_page(mm, (0, ch_id, z_id), reader.read(path, page))
 
 
 def warp_and_save_pages(mm, reader: PageReader, flow: torch.Tensor, jobs, tile_size: int, overlap: int):
@@ -136,7 +143,7 @@ def warp_and_save_pages(mm, reader: PageReader, flow: torch.Tensor, jobs, tile_s
     def drain(item):
         ch_id, z_id, s, host, _keep = item
         s.synchronize()
-        mm[0, ch_id, z_id, :, :] = host.numpy()
+        tiffio.write_page(mm, (0, ch_id, z_id), host.numpy())
 
     for i, k in enumerate(_my_share(len(jobs))):
         ch_id, z_id, path, page = jobs[k]
@@ -227,6 +234,7 @@ def register_and_save_ofreg_imgs(dataset_struct: DatasetStruct, out_dir: Path, f
         _barrier()
         del img_memmap
     reader.close()
+    tiffio.close_writers()
     return decisions
 
 

@@ -225,3 +225,27 @@ def test_page_array_outlives_the_file(tmp_path):
     with tiffio.TiffFile(single) as tif:
         one = tif.asarray()
     assert np.array_equal(one, a[0, 0, 1]) and int(one.sum()) == int(a[0, 0, 1].astype(np.int64).sum())
+
+
+def test_threaded_copy_and_page_writer(tmp_path):
+    """copy_rows (threaded row copy for large pages) and write_page (pwrite behind a memory-mapped stack) are plain copies."""
+    rng = np.random.default_rng(3)
+    big = rng.integers(0, 65535, (6000, 6000)).astype(np.uint16)          # 72 MB: takes the threaded path
+    dst = np.zeros_like(big)
+    tiffio.copy_rows(dst, big)
+    assert np.array_equal(dst, big)
+    p = tmp_path / "stack.tif"
+    a = np.stack(pages(6)).reshape(1, 2, 3, 50, 70)
+    mm = tiffio.memmap(p, a.shape, a.dtype)
+    for c in range(2):
+        for z in range(3):
+            tiffio.write_page(mm, (0, c, z), a[0, c, z])
+    assert np.array_equal(np.asarray(mm), a)          # the mapping sees what pwrite wrote
+    mm.flush()
+    del mm
+    tiffio.close_writers()
+    with tiffio.TiffFile(p) as tif:
+        assert np.array_equal(tif.asarray().reshape(a.shape), a)
+    plain = np.zeros((2, 50, 70), np.uint16)          # not a memmap: falls back to an assignment
+    tiffio.write_page(plain, (1,), a[0, 0, 0])
+    assert np.array_equal(plain[1], a[0, 0, 0])
