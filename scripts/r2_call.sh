@@ -1,13 +1,8 @@
 #!/bin/bash
-set -u
-mkdir -p gpurun_out
-echo "== pipeline bench C4, 8 GPUs"
-timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29517 scripts/bench_pipeline.py > gpurun_out/r2c25_c4_8gpu.json 2> gpurun_out/r2c25_c4_8gpu.err; tail -c 1300 gpurun_out/r2c25_c4_8gpu.json; grep -v "Warn\|warn\|^$\|\*\*\*\|OMP_NUM" gpurun_out/r2c25_c4_8gpu.err | tail -5
-echo "== bench 8 GPUs 50000"
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 8 > gpurun_out/r2c25_bench_8gpu_50000.json 2> gpurun_out/r2c25_bench_8gpu_50000.err; grep "microaligner_b200:\|Error\|error" gpurun_out/r2c25_bench_8gpu_50000.err | head -5
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 4 > gpurun_out/r2c27_bench_4gpu_50000.json 2> gpurun_out/r2c27_bench_4gpu_50000.err; grep "microaligner_b200:\|Error\|error" gpurun_out/r2c27_bench_4gpu_50000.err | head -5
 python - <<'PY'
 import json
-for f in ['r2c25_bench_8gpu_50000']:
+for f in ['r2c27_bench_4gpu_50000']:
     try:
         d=json.loads(open(f'gpurun_out/{f}.json').read().strip().splitlines()[-1])
         print(f,'value',round(d['value'],1),'ms',round(d['ms_per_step'],2),'e2e',round(d['e2e']['value'],1),round(d['e2e']['ms_per_step'],2), d['parity'])
