@@ -128,6 +128,10 @@ class Engine:
         # rows of the final flow are handed to a host sink as soon as they are final; on one GPU the last level runs its
         # Farneback tile row by tile row and merges / downloads speculatively behind it (see register())
         self.stream_groups = True
+        # A level's accept / reject decision is read back from the device only after the NEXT level's warp and DoG images
+        # have been enqueued on the assumption "accepted", so the device queue does not run dry at every level
+        # (MA_DEFER_GATE=0: read it back at once).  Results do not depend on it.
+        self.defer_gate = os.environ.get("MA_DEFER_GATE", "1") not in ("", "0")
         self.gather_pieces = 4       # pieces in which a sharded warp() sends its band to the other ranks
         self.group_tiles = 40        # tiles per Farneback launch of that streamed last level (enough CTAs to fill 148 SMs)
         self.flow_layout = None
@@ -141,6 +145,9 @@ class Engine:
     # in Engine.times -- bench.py prints it as `phases_ms`.
     trace = False
     times = defaultdict(float)
+    # Engine.timeline = [] records, without synchronising, when the host entered / left every phase and a device event at
+    # both points (scripts/timeline.py lines them up: where the device waits for the host or for a peer).
+    timeline = None
 
     @contextlib.contextmanager
     def phase(self, name):
@@ -148,6 +155,16 @@ class Engine:
         if nvtx is not None:
             nvtx.range_push("ma:" + name)
         try:
+            if Engine.timeline is not None:     # no synchronisation: CPU enqueue times and device events per phase
+                rec = [name, time.perf_counter(), torch.cuda.Event(enable_timing=True), None, torch.cuda.Event(enable_timing=True)]
+                rec[2].record()
+                Engine.timeline.append(rec)
+                try:
+                    yield
+                finally:
+                    rec[3] = time.perf_counter()
+                    rec[4].record()
+                return
             if not Engine.trace:
                 yield
                 return
@@ -254,58 +271,96 @@ class Engine:
             pyr.append(arr)
         return pyr
 
-    def dog_batch(self, items, L: LevelLayout) -> List[torch.Tensor]:
-        """uint8 DoG of several images of one level: items = [(img, rows)], result i valid on rows_i.
-        Sharded levels need the GLOBAL min/max of every source and of every difference image: every rank
+    def dog_batch(self, items, L: Optional[LevelLayout] = None) -> List[torch.Tensor]:
+        """uint8 DoG of several images: items = [(img, rows)] of level L or [(img, rows, level)], result i valid on
+        rows_i.  Sharded levels need the GLOBAL min/max of every source and of every difference image: every rank
         scans its own band, and all pairs of the batch travel in ONE all-reduce per phase."""
+        items = [(it[0], it[1], it[2] if len(it) > 2 else L) for it in items]
         k = len(items)
         dev = items[0][0].device
+        sharded = any(Li.sharded for _, _, Li in items)
         mm = torch.empty((k, 2), dtype=torch.float32, device=dev)
         dmm = torch.empty((k, 2), dtype=torch.float32, device=dev)
-        for i, (img, rows) in enumerate(items):
-            ops.minmax_rows(img, L.band if L.sharded else (0, L.h), out=mm[i])
-        if L.sharded:
+        for i, (img, rows, Li) in enumerate(items):
+            ops.minmax_rows(img, Li.band if Li.sharded else (0, Li.h), out=mm[i])
+        if sharded:
             self.comm.allreduce_minmax(mm)
-        diffs = [ops.dog_diff_rows(img, mm[i], rows, dmm=dmm[i])[0] for i, (img, rows) in enumerate(items)]
-        if L.sharded:
+        diffs = [ops.dog_diff_rows(img, mm[i], rows, dmm=dmm[i])[0] for i, (img, rows, Li) in enumerate(items)]
+        if sharded:
             self.comm.allreduce_minmax(dmm)
         outs = []
-        for i, (img, rows) in enumerate(items):
-            out = torch.empty((L.h, L.w), dtype=torch.uint8, device=dev)
-            outs.append(ops.dog_quantize_rows(diffs[i], L.h, L.w, dmm[i], rows, out))
+        for i, (img, rows, Li) in enumerate(items):
+            out = torch.empty((Li.h, Li.w), dtype=torch.uint8, device=dev)
+            outs.append(ops.dog_quantize_rows(diffs[i], Li.h, Li.w, dmm[i], rows, out))
+            diffs[i] = None
         return outs
+
+    def level_rows(self, L: LevelLayout):
+        """Row ranges of a level on this rank: (gate_rows, fb_rows, ref_dog_rows, over) -- the rows the similarity gate
+        reads (the band plus what its last NMI chunk runs past it), the rows this rank's Farneback tiles read, the rows
+        of the reference DoG image that serve both, and the gate's overrun."""
+        B = L.band
+        over = -(-self.T * self.T // L.w) + 1 if L.tiled else 0
+        gate_rows = _clip(B[0], B[1] + over, L.h) if L.sharded else (0, L.h)
+        if B[1] <= B[0]:                                       # more ranks than tile rows: nothing to do here
+            gate_rows = (B[0], B[0])
+        fb_rows = L.fb_window_rows()[L.rank] if L.sharded else (0, L.h)
+        ref_dog_rows = gate_rows
+        if self.use_dog and fb_rows[1] > fb_rows[0]:
+            ref_dog_rows = _union(gate_rows, fb_rows) if gate_rows[1] > gate_rows[0] else fb_rows
+        return gate_rows, fb_rows, ref_dog_rows, over
 
     def warp_rows(self, img: torch.Tensor, flow: torch.Tensor, L: LevelLayout, rows: Range) -> torch.Tensor:
         out = torch.empty_like(img)
         return ops.warp_tiles_rows(img, flow, self.T, self.ov, rows, out)
 
-    def mi_scores(self, a: torch.Tensor, bs: Sequence[torch.Tensor], L: LevelLayout) -> List[float]:
-        """mi_tiled(a, b) for every b in bs (similarity_scoring.py:27-50): per-chunk NMI on the device, one
-        all-reduce and one read-back for the whole batch, np.mean on the host (rounds like the reference)."""
+    def mi_scores_async(self, a: torch.Tensor, bs: Sequence[torch.Tensor], L: LevelLayout):
+        """mi_tiled(a, b) for every b in bs (similarity_scoring.py:27-50): per-chunk NMI on the device, one all-reduce
+        and one read-back for the whole batch, np.mean on the host (rounds like the reference).  Everything is enqueued
+        here; the returned callable waits for the read-back and returns the scores."""
         n = a.numel()
         if not L.tiled:
-            return [float(ops.nmi_chunks(a, b, n).cpu().numpy()[0]) for b in bs]
-        chunk = self.T * self.T
-        nchunks = -(-n // chunk)
-        scores = torch.zeros((len(bs), nchunks), dtype=torch.float64, device=a.device)
-        cr = parallel.chunk_range_of_band(L.band, L.w, chunk, n) if L.sharded else (0, nchunks)
-        if len(bs) == 2:
-            ops.nmi_chunk_range2(a, bs[0], bs[1], chunk, cr, scores[0], scores[1])
+            scores = torch.stack([ops.nmi_chunks(a, b, n)[:1] for b in bs])
         else:
-            for i, b in enumerate(bs):
-                ops.nmi_chunk_range(a, b, chunk, cr, scores[i])
-        if L.sharded:
-            self.comm.allreduce_sum(scores)
-        host = scores.cpu().numpy()
-        return [float(np.mean(host[i])) for i in range(len(bs))]
+            chunk = self.T * self.T
+            nchunks = -(-n // chunk)
+            scores = torch.zeros((len(bs), nchunks), dtype=torch.float64, device=a.device)
+            cr = parallel.chunk_range_of_band(L.band, L.w, chunk, n) if L.sharded else (0, nchunks)
+            if len(bs) == 2:
+                ops.nmi_chunk_range2(a, bs[0], bs[1], chunk, cr, scores[0], scores[1])
+            else:
+                for i, b in enumerate(bs):
+                    ops.nmi_chunk_range(a, b, chunk, cr, scores[i])
+            if L.sharded:
+                self.comm.allreduce_sum(scores)
+        done = None
+        if scores.is_cuda:
+            host = torch.empty(scores.shape, dtype=scores.dtype, pin_memory=True)
+            host.copy_(scores, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+        else:
+            host = scores
+
+        def result() -> List[float]:
+            if done is not None:
+                done.synchronize()
+            arr = host.numpy()
+            return [float(np.mean(arr[i])) for i in range(len(bs))]
+        return result
+
+    def mi_scores(self, a: torch.Tensor, bs: Sequence[torch.Tensor], L: LevelLayout) -> List[float]:
+        return self.mi_scores_async(a, bs, L)()
 
     def pyr_up(self, flow: torch.Tensor, Ls: LevelLayout, Ld: LevelLayout, scale: float) -> torch.Tensor:
-        """cv.pyrUp(flow*scale) from level Ls to level Ld; every rank produces the rows of its Ld band."""
+        """cv.pyrUp(flow*scale) from level Ls to level Ld; every rank produces the rows of its Ld band plus the `ov` rows
+        on either side that its tile windows cover (what the merge at level Ld reads), from source rows fetched once."""
         out = torch.empty((Ld.h, Ld.w, 2), dtype=torch.float32, device=flow.device)
+        rows = Ld.grow(self.ov, self.ov)
         if Ls.sharded:
-            need = [_clip(a // 2 - 2, (b + 1) // 2 + 2, Ls.h) if b > a else (0, 0) for a, b in Ld.bands]
+            need = [_clip(a // 2 - 2, (b + 1) // 2 + 2, Ls.h) if b > a else (0, 0) for a, b in rows]
             self.comm.exchange_rows(flow, Ls.bands, need)
-        return ops.pyr_up_flow_rows(flow, (Ld.h, Ld.w), scale, Ld.band, out)
+        return ops.pyr_up_flow_rows(flow, (Ld.h, Ld.w), scale, rows[Ld.rank], out)
 
     # ------------------------------------------------------------------ register()
     def register(self, ref: torch.Tensor, mov: torch.Tensor, sink=None, ready=(None, None)) -> torch.Tensor:
@@ -334,8 +389,17 @@ class Engine:
         self.decisions = []
         m_flow, m_layout = None, None
 
+        # The DoG images of the similarity gate -- reference and unwarped moving image of every level -- depend on no flow:
+        # all levels go through one batch here, i.e. two all-reduces for the whole pyramid instead of two per level.
+        with self.phase("dog"):
+            items = []
+            for k, Lk in enumerate(layouts):
+                g_rows, _, r_rows, _ = self.level_rows(Lk)
+                items += [(ref_pyr[k], r_rows, Lk), (mov_pyr[k], g_rows, Lk)]
+            gate_dogs = self.dog_batch(items) if items else []
+            del items
+        pending = None       # the previous level's gate: enqueued, assumed to accept, not read back yet
         for lvl, factor in enumerate(factors):
-            self.log("Pyramid factor", factor)
             nvtx = _nvtx()
             if nvtx is not None:
                 if lvl > 0:
@@ -344,43 +408,44 @@ class Engine:
             L = layouts[lvl]
             B = L.band
             halo = ov + (20 if self.use_dog else 0)
-            over = -(-T * T // L.w) + 1 if L.tiled else 0          # rows an NMI chunk may run past the band
-            gate_rows = _clip(B[0], B[1] + over, L.h) if L.sharded else (0, L.h)
-            win_rows = _clip(B[0] - ov, B[1] + ov, L.h) if L.sharded else (0, L.h)
-            if B[1] <= B[0]:                                       # more ranks than tile rows: nothing to do here
-                gate_rows = win_rows = (B[0], B[0])
-            fb_rows = L.fb_window_rows()[L.rank] if L.sharded else (0, L.h)   # rows my Farneback tiles read
+            gate_rows, fb_rows, _, over = self.level_rows(L)
+            ref_dog, od = gate_dogs[2 * lvl], gate_dogs[2 * lvl + 1]
+            gate_dogs[2 * lvl] = gate_dogs[2 * lvl + 1] = None
 
-            mov_l = mov_pyr[lvl]
-            mov_banded = False
-            if lvl > 0:
-                if L.sharded:
-                    with self.phase("exchange"):
-                        comm.exchange_rows(m_flow, L.bands, L.grow(ov, ov))      # merge reads tile windows
-                with self.phase("warp"):
-                    mov_l = self.warp_rows(mov_l, m_flow, L, B)
-                mov_banded = L.sharded
-                if L.sharded:
-                    dh = 20 if self.use_dog else 0
-                    need = [b if a[1] <= a[0] else (_union(a, b) if b[1] > b[0] else a)
-                            for a, b in zip(L.grow(halo, halo), L.fb_window_rows(dh))]
-                    with self.phase("exchange"):
-                        comm.exchange_rows(mov_l, L.bands, need)
+            def head(m_flow, lvl=lvl, L=L, B=B, halo=halo, fb_rows=fb_rows, ref_dog=ref_dog):
+                """Everything of this level in front of Farneback: pre-warp by the accumulated flow, its DoG image."""
+                mov_l = mov_pyr[lvl]
+                if lvl > 0:           # m_flow: from pyr_up(), i.e. valid on the band and the overlap of its tile windows
+                    with self.phase("warp"):
+                        mov_l = self.warp_rows(mov_l, m_flow, L, B)
+                    if L.sharded:
+                        dh = 20 if self.use_dog else 0
+                        need = [b if a[1] <= a[0] else (_union(a, b) if b[1] > b[0] else a)
+                                for a, b in zip(L.grow(halo, halo), L.fb_window_rows(dh))]
+                        with self.phase("exchange"):
+                            comm.exchange_rows(mov_l, L.bands, need)
+                if not self.use_dog:
+                    return mov_l, ref_pyr[lvl], mov_l
+                with self.phase("dog"):
+                    return mov_l, ref_dog, self.dog_batch([(mov_l, fb_rows)], L)[0]
 
-            # the reference DoG image serves the flow (if use_dog) and the gate (always)
-            ref_dog_rows = gate_rows
-            if self.use_dog and fb_rows[1] > fb_rows[0]:
-                ref_dog_rows = _union(gate_rows, fb_rows) if gate_rows[1] > gate_rows[0] else fb_rows
-            with self.phase("dog"):
-                # batch 1: everything that does not depend on this level's flow
-                items = [(ref_pyr[lvl], ref_dog_rows), (mov_pyr[lvl], gate_rows)]
-                if self.use_dog:
-                    items.append((mov_l, fb_rows))
-                dogs = self.dog_batch(items, L)
-                ref_dog, od = dogs[0], dogs[1]
-                fb_ref = ref_dog if self.use_dog else ref_pyr[lvl]
-                fb_mov = dogs[2] if self.use_dog else mov_l
-                del dogs, items
+            # The head of this level is enqueued behind the previous level's gate BEFORE that gate is read back, on the
+            # assumption that it accepted (it nearly always does): the host only blocks once the device has this much
+            # work queued, so the device does not run dry at every level while the host catches up.  A rejected level
+            # costs the head twice.
+            state = head(m_flow)
+            if pending is not None:
+                gate, p_lvl, p_flow, p_layout = pending
+                pending = None
+                if not self._judge(gate, factors[p_lvl], p_lvl):
+                    del state
+                    with self.phase("merge+pyrup"):
+                        m_flow, m_layout = self._rejected(p_lvl, p_flow, p_layout, L, ref.device), L
+                    state = head(m_flow)
+                del gate, p_flow
+            self.log("Pyramid factor", factor)
+            mov_l, fb_ref, fb_mov = state
+            del state
             this_flow = torch.empty((L.h, L.w, 2), dtype=torch.float32, device=ref.device)
             # Speculative tail of the LAST level: if the gate accepts this level -- it nearly always does -- the result is
             # merge(m_flow, this_flow), which is per tile.  So this rank's Farneback tiles run one group of tile rows at a
@@ -435,19 +500,19 @@ class Engine:
                 wd = self.dog_batch([(warped, gate_rows)], L)[0]
             del warped
             with self.phase("nmi gate"):
-                after, before = self.mi_scores(ref_dog, [wd, od], L)
+                gate = self.mi_scores_async(ref_dog, [wd, od], L)
             del ref_dog, wd, od
-            self.log("    MI score after:", after, "| MI score before:", before)
-            better = after > before
-            if self.force_decisions is not None:      # test hook: exercise the "Worse alignment" branches
-                better = bool(self.force_decisions[lvl])
-            self.decisions.append(dict(factor=factor, mi_after=after, mi_before=before, better=better))
             Ln = layouts[lvl + 1] if lvl + 1 < num_lvl else None
+            if self.defer_gate and Ln is not None:
+                better = True                                      # read back behind the next level's head
+                pending = (gate, lvl, m_flow, L)
+            else:
+                better = self._judge(gate, factor, lvl)
+            del gate
 
             tail = self.phase("merge+pyrup")
             tail.__enter__()
             if better:
-                self.log("    Better alignment than before")
                 if lvl == 0:
                     if num_lvl > 1:
                         m_flow, m_layout = self.pyr_up(this_flow, L, Ln, 2.0), Ln
@@ -469,17 +534,12 @@ class Engine:
                 else:
                     merged = self._merge(m_flow, this_flow, L)
                     m_flow, m_layout = self.pyr_up(merged, L, Ln, 2.0), Ln
-            else:
-                self.log("    Worse alignment than before")
-                if lvl == 0:
-                    shape = (Ln.h, Ln.w) if num_lvl > 1 else tuple(mov.shape)
-                    m_flow = torch.zeros(shape + (2,), dtype=torch.float32, device=ref.device)
-                    m_layout = Ln if num_lvl > 1 else full
-                elif lvl == num_lvl - 1:
-                    if not self.full_res:
-                        m_flow, m_layout = self.pyr_up(m_flow, L, full, 2.0), full
-                else:
-                    m_flow, m_layout = self.pyr_up(m_flow, L, Ln, 4.0), Ln
+            elif Ln is not None:
+                m_flow, m_layout = self._rejected(lvl, m_flow, L, Ln, ref.device), Ln
+            elif lvl == 0:
+                m_flow, m_layout = torch.zeros(tuple(mov.shape) + (2,), dtype=torch.float32, device=ref.device), full
+            elif not self.full_res:
+                m_flow, m_layout = self.pyr_up(m_flow, L, full, 2.0), full
             tail.__exit__(None, None, None)
             del this_flow
 
@@ -495,6 +555,23 @@ class Engine:
             with self.phase("gather flow"):
                 comm.gather_rows(m_flow, m_layout.bands)
         return m_flow
+
+    def _judge(self, gate, factor: int, lvl: int) -> bool:
+        """Read a level's gate back and record the decision (optflow_registrator.py:150-171)."""
+        after, before = gate()
+        self.log("    MI score after:", after, "| MI score before:", before)
+        better = after > before
+        if self.force_decisions is not None:      # test hook: exercise the "Worse alignment" branches
+            better = bool(self.force_decisions[lvl])
+        self.decisions.append(dict(factor=factor, mi_after=after, mi_before=before, better=better))
+        self.log("    Better alignment than before" if better else "    Worse alignment than before")
+        return better
+
+    def _rejected(self, lvl: int, m_flow, L: LevelLayout, Ln: LevelLayout, device) -> torch.Tensor:
+        """The accumulated flow handed to level lvl+1 when level lvl is rejected (optflow_registrator.py:160-171)."""
+        if lvl == 0:
+            return torch.zeros((Ln.h, Ln.w, 2), dtype=torch.float32, device=device)
+        return self.pyr_up(m_flow, L, Ln, 4.0)
 
     def _merge(self, m_flow: torch.Tensor, this_flow: torch.Tensor, L: LevelLayout) -> torch.Tensor:
         out = torch.empty_like(this_flow)

@@ -20,6 +20,9 @@ class Warper:
         self.tile_size = 1000
         self.overlap = 100
         self._slicer_info = {}
+        # several ranks, CUDA tensors: True = every rank returns the whole image (its band is warped locally, the other
+        # bands arrive over NVLink); False = the result is valid on Engine.warp_band() -- this rank's rows -- only
+        self.gather_image = True
 
     def warp(self):
         image, flow = self.image, self.flow
@@ -28,7 +31,7 @@ class Warper:
         comm = parallel.get()
         if isinstance(image, torch.Tensor):
             flow = ops.to_device(flow, image.device)
-            return Engine(self.tile_size, self.overlap, comm=comm).warp(ops.to_device(image), flow)
+            return Engine(self.tile_size, self.overlap, comm=comm).warp(ops.to_device(image), flow, gather=self.gather_image)
         image = np.asarray(image)
         if image.ndim != 2 or image.dtype not in (np.uint8, np.uint16):
             raise TypeError(f"unsupported image: dtype {image.dtype}, {image.ndim} dimensions; expected 2-D uint8 or uint16")

@@ -145,6 +145,7 @@ class Comm:
         self.backend = dist.get_backend(group) if group is not None else None
         # ranks in this module are GROUP ranks; P2POp / broadcast address peers by GLOBAL rank
         self._global = [dist.get_global_rank(group, r) for r in range(self.world)] if group is not None else [0]
+        self._sign = {}      # device -> [-1, 1] (allreduce_minmax)
 
     # -- layout ---------------------------------------------------------------------------------
     def tile_row_bands(self, ny: int) -> List[Range]:
@@ -230,9 +231,11 @@ class Comm:
         """mm = (..., 2) float32 [min, max] pairs (device); reduced in place over the group, one collective."""
         if self.world == 1:
             return mm
-        v = torch.stack([-mm[..., 0], mm[..., 1]])
-        v = self._allreduce(v, dist.ReduceOp.MAX)
-        mm[..., 0], mm[..., 1] = -v[0], v[1]
+        sign = self._sign.get(mm.device)
+        if sign is None:
+            sign = self._sign[mm.device] = torch.tensor([-1.0, 1.0], dtype=torch.float32, device=mm.device)
+        v = self._allreduce(mm * sign, dist.ReduceOp.MAX)          # max(-min) = -min(min): one collective for both
+        torch.mul(v, sign, out=mm)
         return mm
 
     def _allreduce(self, t: torch.Tensor, op):

@@ -218,3 +218,59 @@ def test_speculative_streaming_on_one_rank(forced):
             assert log == speculated
     finally:
         engine.ops, engine.torch = saved
+
+
+DEFER_CASE = ((520, 610), np.uint16, dict(tile_size=100, overlap=16, num_pyr_lvl=2, num_iterations=1, use_full_res_img=True,
+                                          use_dog=True))
+
+
+def _run_deferred(ref, mov, kw, forced, defer):
+    from microaligner_b200 import engine, parallel
+    from tests import mock_ops
+    saved = engine.ops, engine.torch
+    engine.ops, engine.torch = mock_ops, _PoisonTorch()
+    try:
+        lines = []
+        eng = engine.Engine(kw["tile_size"], kw["overlap"], kw["num_pyr_lvl"], kw["num_iterations"], kw["use_full_res_img"],
+                            kw["use_dog"], comm=parallel.get(), log=lambda *a: lines.append(" ".join(str(x) for x in a)))
+        eng.force_decisions, eng.defer_gate = forced, defer
+        flow = eng.register(torch.from_numpy(ref), torch.from_numpy(mov))
+        return flow.numpy().copy(), [d["better"] for d in eng.decisions], lines
+    finally:
+        engine.ops, engine.torch = saved
+
+
+def _worker_deferred(rank, world, port, tmp, forced):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from microaligner_b200 import parallel
+    parallel.init(dist.group.WORLD)
+    try:
+        shape, dtype, kw = DEFER_CASE
+        ref, mov = synth_pair(shape[0], shape[1], 3, dtype, amp=2.0, period=160.0)
+        flow, dec, lines = _run_deferred(ref, mov, kw, forced, True)
+        np.savez(os.path.join(tmp, f"r{rank}.npz"), flow=flow, dec=np.array(dec), lines=np.array(lines))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("forced", [None, (False, True, True), (True, False, True), (False, False, False)])
+def test_deferred_gate_equals_immediate_gate(tmp_path, forced):
+    """The accept / reject decision of a level is read back behind the next level's pre-warp and DoG images, which are
+    enqueued assuming "accepted".  A rejected level (forced here) redoes them from the right flow: flow, decisions and
+    the order of the log lines equal those of the run that reads every gate at once -- on one rank and on two."""
+    shape, dtype, kw = DEFER_CASE
+    ref, mov = synth_pair(shape[0], shape[1], 3, dtype, amp=2.0, period=160.0)
+    want = _run_deferred(ref, mov, kw, forced, False)
+    got = _run_deferred(ref, mov, kw, forced, True)
+    assert len(want[1]) == 3 and got[1] == want[1] and got[2] == want[2]
+    order = [ln.strip().split()[0] for ln in got[2]]
+    assert order == ["Pyramid", "MI", "Better" if got[1][0] else "Worse", "Pyramid", "MI", "Better" if got[1][1] else "Worse",
+                     "Pyramid", "MI", "Better" if got[1][2] else "Worse"]
+    assert np.array_equal(got[0], want[0])
+    if forced is not None:
+        mp.spawn(_worker_deferred, args=(2, _free_port(), str(tmp_path), forced), nprocs=2, join=True)
+        for r in range(2):
+            res = np.load(tmp_path / f"r{r}.npz")
+            assert list(res["dec"]) == want[1] and list(res["lines"]) == (want[2] if r == 0 else [])     # rank 0 reports
+            assert np.array_equal(res["flow"], want[0]), f"rank {r}: flow differs"
