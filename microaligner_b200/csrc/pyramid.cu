@@ -32,6 +32,57 @@ __global__ void __launch_bounds__(256) pyrdown_kernel(const T* __restrict__ src,
     *((T*)((char*)dst + (size_t)oy * dp) + ox) = (T)((acc + 128) >> 8);
 }
 
+// Default: a thread owns one output column and marches down kPdRows output rows.  Every source row is reduced
+// horizontally ONCE (the one-output-per-thread kernel above does it 2.5 times) from three aligned pair loads -- pixels
+// (2x-2, 2x-1), (2x, 2x+1), (2x+2, 2x+3), consecutive words across the warp -- and kept in a five-deep rolling window
+// of registers.  Columns whose taps leave the row take the scalar REFLECT_101 path.  Integer sums: bit-exact.
+constexpr int kPdRows = 32, kPdThreads = 128;
+
+template <typename T> struct PairOf;
+template <> struct PairOf<uint8_t> { using type = unsigned short; };
+template <> struct PairOf<uint16_t> { using type = unsigned int; };
+
+template <typename T>
+__global__ void __launch_bounds__(kPdThreads) pyrdown_march_kernel(const T* __restrict__ src, size_t sp, int h, int w,
+                                                                   T* __restrict__ dst, size_t dp, int oh, int ow, int ybeg) {
+    using P = typename PairOf<T>::type;
+    constexpr int kBits = 8 * (int)sizeof(T);
+    constexpr unsigned kMask = (1u << kBits) - 1u;
+    const int ox = blockIdx.x * kPdThreads + threadIdx.x;
+    const int oy0 = ybeg + blockIdx.y * kPdRows;
+    if (ox >= ow || oy0 >= oh) return;
+    const int oy1 = min(oy0 + kPdRows, oh);
+    const int cx = 2 * ox;
+    const bool interior = cx >= 3 && cx + 3 < w;       // both pair alignments stay inside the row
+    int xs[5];
+#pragma unroll
+    for (int d = 0; d < 5; ++d) xs[d] = reflect101(cx + d - 2, w);
+    auto hrow = [&](int y) -> int {
+        const T* row = (const T*)((const char*)src + (size_t)reflect101(y, h) * sp);
+        if (interior) {
+            if (((size_t)row & (sizeof(P) - 1)) == 0) {          // pairs (cx-2, cx-1) (cx, cx+1) (cx+2, cx+3)
+                const P* q = (const P*)(row + cx - 2);
+                const unsigned a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+                return (int)(a & kMask) + 4 * (int)(a >> kBits) + 6 * (int)(b & kMask) + 4 * (int)(b >> kBits) + (int)(c & kMask);
+            }
+            const P* q = (const P*)(row + cx - 3);               // row starts mid-pair: (cx-3, cx-2) (cx-1, cx) (cx+1, cx+2)
+            const unsigned a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+            return (int)(a >> kBits) + 4 * (int)(b & kMask) + 6 * (int)(b >> kBits) + 4 * (int)(c & kMask) + (int)(c >> kBits);
+        }
+        return (int)__ldg(row + xs[0]) + 4 * (int)__ldg(row + xs[1]) + 6 * (int)__ldg(row + xs[2]) +
+               4 * (int)__ldg(row + xs[3]) + (int)__ldg(row + xs[4]);
+    };
+    int r0 = hrow(2 * oy0 - 2), r1 = hrow(2 * oy0 - 1), r2 = hrow(2 * oy0);
+#pragma unroll 2
+    for (int oy = oy0; oy < oy1; ++oy) {
+        const int r3 = hrow(2 * oy + 1), r4 = hrow(2 * oy + 2);
+        *((T*)((char*)dst + (size_t)oy * dp) + ox) = (T)((r0 + 4 * r1 + 6 * r2 + 4 * r3 + r4 + 128) >> 8);
+        r0 = r2;
+        r1 = r3;
+        r2 = r4;
+    }
+}
+
 __device__ __forceinline__ float2 mul2(float2 a, float s) { return make_float2(__fmul_rn(a.x, s), __fmul_rn(a.y, s)); }
 __device__ __forceinline__ float2 add2(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
 
@@ -96,15 +147,23 @@ extern "C" int ma_pyrdown_rows(const void* src, size_t src_pitch, int h, int w, 
     int oh = (h + 1) / 2, ow = (w + 1) / 2;
     if (row_begin < 0 || row_end > oh || row_begin > row_end) return invalid("ma_pyrdown: bad row range");
     if (row_begin == row_end) return MA_OK;
-    dim3 block(32, 8), grid(ceil_div(ow, 32), ceil_div(row_end - row_begin, 8));
     cudaStream_t s = (cudaStream_t)stream;
+    if (dtype != MA_U8 && dtype != MA_U16) return invalid("ma_pyrdown: dtype must be MA_U8 or MA_U16");
     KernelScope ks(K_PYRDOWN, s, 4.0 * (row_end - row_begin) * ow);
-    if (dtype == MA_U8)
-        pyrdown_kernel<uint8_t><<<grid, block, 0, s>>>((const uint8_t*)src, src_pitch, h, w, (uint8_t*)dst, dst_pitch, row_end, ow, row_begin);
-    else if (dtype == MA_U16)
-        pyrdown_kernel<uint16_t><<<grid, block, 0, s>>>((const uint16_t*)src, src_pitch, h, w, (uint16_t*)dst, dst_pitch, row_end, ow, row_begin);
-    else
-        return invalid("ma_pyrdown: dtype must be MA_U8 or MA_U16");
+    static const bool simple = getenv("MA_PYRDOWN_SIMPLE") != nullptr;      // the one-output-per-thread kernel (A/B)
+    if (simple) {
+        dim3 block(32, 8), grid(ceil_div(ow, 32), ceil_div(row_end - row_begin, 8));
+        if (dtype == MA_U8)
+            pyrdown_kernel<uint8_t><<<grid, block, 0, s>>>((const uint8_t*)src, src_pitch, h, w, (uint8_t*)dst, dst_pitch, row_end, ow, row_begin);
+        else
+            pyrdown_kernel<uint16_t><<<grid, block, 0, s>>>((const uint16_t*)src, src_pitch, h, w, (uint16_t*)dst, dst_pitch, row_end, ow, row_begin);
+    } else {
+        dim3 grid(ceil_div(ow, kPdThreads), ceil_div(row_end - row_begin, kPdRows));
+        if (dtype == MA_U8)
+            pyrdown_march_kernel<uint8_t><<<grid, kPdThreads, 0, s>>>((const uint8_t*)src, src_pitch, h, w, (uint8_t*)dst, dst_pitch, row_end, ow, row_begin);
+        else
+            pyrdown_march_kernel<uint16_t><<<grid, kPdThreads, 0, s>>>((const uint16_t*)src, src_pitch, h, w, (uint16_t*)dst, dst_pitch, row_end, ow, row_begin);
+    }
     MA_LAUNCH_CHECK("pyrdown_kernel");
     return MA_OK;
 }
