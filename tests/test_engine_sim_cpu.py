@@ -49,7 +49,7 @@ class _PoisonTorch:
         return self._poison(torch.empty_like(*a, **k))
 
 
-def _run(ref, mov, kw, local_pyramid=False, corrected=False):
+def _run(ref, mov, kw, local_pyramid=False, corrected=False, forced=None):
     from microaligner_b200 import engine, parallel
     from tests import mock_ops
     saved = engine.ops, engine.torch
@@ -58,6 +58,7 @@ def _run(ref, mov, kw, local_pyramid=False, corrected=False):
         eng = engine.Engine(kw["tile_size"], kw["overlap"], kw["num_pyr_lvl"], kw["num_iterations"], kw["use_full_res_img"],
                             kw["use_dog"], comm=parallel.get(), log=lambda *a: None, corrected=corrected)
         eng.local_pyramid = local_pyramid
+        eng.force_decisions = forced
         flow = eng.register(torch.from_numpy(ref), torch.from_numpy(mov))
         img = eng.warp(torch.from_numpy(mov), flow)
         return flow.numpy().copy(), img.numpy().copy(), [d["better"] for d in eng.decisions]
@@ -123,7 +124,7 @@ def test_sharded_engine_corner_cases(tmp_path, world, case, corrected, gather_be
         assert np.array_equal(got["flow"], want_flow) and np.array_equal(got["img"], want_img), f"rank {r} differs"
 
 
-def _worker_host(rank, world, port, case, tmp):
+def _worker_host(rank, world, port, case, tmp, forced=None):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from microaligner_b200 import engine, parallel
@@ -136,6 +137,7 @@ def _worker_host(rank, world, port, case, tmp):
         eng = engine.Engine(kw["tile_size"], kw["overlap"], kw["num_pyr_lvl"], kw["num_iterations"], kw["use_full_res_img"],
                             kw["use_dog"], comm=parallel.get(), log=lambda *a: None)
         eng.group_tiles = 1             # one tile row per group: the speculative streaming of the last level is exercised
+        eng.force_decisions = forced
         sinks, real = [], mock_ops.HostSink
         mock_ops.HostSink = lambda host: sinks.append(real(host)) or sinks[-1]
         for rep in range(2):            # the second round reuses the node-shared result blocks of the first
@@ -172,6 +174,23 @@ def test_host_io_on_several_ranks(tmp_path, case, world):
             assert len(pushes) >= 2 and len(set(pushes)) == len(pushes), pushes
             rows = sorted(pushes)
             assert all(a[1] == b[0] for a, b in zip(rows, rows[1:])), pushes       # this rank's band exactly once
+
+
+@pytest.mark.parametrize("forced", [(True, False), (False, True)])
+def test_host_io_on_two_ranks_with_rejected_levels(tmp_path, forced):
+    """The same with a rejected level: (True, False) -- the rows streamed out speculatively during the last level are all
+    delivered again from the flow that is returned instead; (False, True) -- the first level is rejected after the head
+    of the second was enqueued on the assumption that it would be accepted (deferred gate) and is redone."""
+    case = "tiled levels, dog"
+    shape, dtype, kw = CASES[case]
+    ref, mov = synth_pair(shape[0], shape[1], 3, dtype, amp=2.0, period=160.0)
+    want_flow, want_img, dec = _run(ref, mov, kw, forced=forced)
+    assert dec == list(forced)
+    mp.spawn(_worker_host, args=(2, _free_port(), case, str(tmp_path), forced), nprocs=2, join=True)
+    for r in range(2):
+        got = np.load(tmp_path / f"r{r}_1.npz")
+        assert np.array_equal(got["flow"], want_flow), f"rank {r}: flow differs"
+        assert np.array_equal(got["img"], want_img), f"rank {r}: warped image differs"
 
 
 STREAM_CASE = ((640, 530), np.uint16, dict(tile_size=100, overlap=16, num_pyr_lvl=1, num_iterations=1, use_full_res_img=True,
