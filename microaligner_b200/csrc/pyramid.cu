@@ -42,38 +42,34 @@ template <typename T> struct PairOf;
 template <> struct PairOf<uint8_t> { using type = unsigned short; };
 template <> struct PairOf<uint16_t> { using type = unsigned int; };
 
-template <typename T>
-__global__ void __launch_bounds__(kPdThreads) pyrdown_march_kernel(const T* __restrict__ src, size_t sp, int h, int w,
-                                                                   T* __restrict__ dst, size_t dp, int oh, int ow, int ybeg) {
+// The column loop, compiled once for interior columns (pair loads, no lane-divergent branch: the loads of several
+// source rows are in flight together) and once for columns whose taps leave the row (scalar REFLECT_101 loads).
+template <typename T, bool INTERIOR>
+__device__ __forceinline__ void pyrdown_march(const T* __restrict__ src, size_t sp, int h, int w, T* __restrict__ dst, size_t dp,
+                                              int ox, int oy0, int oy1) {
     using P = typename PairOf<T>::type;
     constexpr int kBits = 8 * (int)sizeof(T);
     constexpr unsigned kMask = (1u << kBits) - 1u;
-    const int ox = blockIdx.x * kPdThreads + threadIdx.x;
-    const int oy0 = ybeg + blockIdx.y * kPdRows;
-    if (ox >= ow || oy0 >= oh) return;
-    const int oy1 = min(oy0 + kPdRows, oh);
     const int cx = 2 * ox;
-    const bool interior = cx >= 3 && cx + 3 < w;       // both pair alignments stay inside the row
     int xs[5];
 #pragma unroll
-    for (int d = 0; d < 5; ++d) xs[d] = reflect101(cx + d - 2, w);
+    for (int d = 0; d < 5; ++d) xs[d] = INTERIOR ? cx + d - 2 : reflect101(cx + d - 2, w);
     auto hrow = [&](int y) -> int {
         const T* row = (const T*)((const char*)src + (size_t)reflect101(y, h) * sp);
-        if (interior) {
-            if (((size_t)row & (sizeof(P) - 1)) == 0) {          // pairs (cx-2, cx-1) (cx, cx+1) (cx+2, cx+3)
-                const P* q = (const P*)(row + cx - 2);
-                const unsigned a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
-                return (int)(a & kMask) + 4 * (int)(a >> kBits) + 6 * (int)(b & kMask) + 4 * (int)(b >> kBits) + (int)(c & kMask);
-            }
-            const P* q = (const P*)(row + cx - 3);               // row starts mid-pair: (cx-3, cx-2) (cx-1, cx) (cx+1, cx+2)
+        if constexpr (INTERIOR) {
+            const bool mid = ((size_t)row & (sizeof(P) - 1)) != 0;      // the row starts in the middle of a pair
+            const P* q = (const P*)(row + cx - (mid ? 3 : 2));
             const unsigned a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
-            return (int)(a >> kBits) + 4 * (int)(b & kMask) + 6 * (int)(b >> kBits) + 4 * (int)(c & kMask) + (int)(c >> kBits);
+            // aligned: (cx-2, cx-1) (cx, cx+1) (cx+2, cx+3);  mid-pair: (cx-3, cx-2) (cx-1, cx) (cx+1, cx+2)
+            return mid ? (int)(a >> kBits) + 4 * (int)(b & kMask) + 6 * (int)(b >> kBits) + 4 * (int)(c & kMask) + (int)(c >> kBits)
+                       : (int)(a & kMask) + 4 * (int)(a >> kBits) + 6 * (int)(b & kMask) + 4 * (int)(b >> kBits) + (int)(c & kMask);
+        } else {
+            return (int)__ldg(row + xs[0]) + 4 * (int)__ldg(row + xs[1]) + 6 * (int)__ldg(row + xs[2]) +
+                   4 * (int)__ldg(row + xs[3]) + (int)__ldg(row + xs[4]);
         }
-        return (int)__ldg(row + xs[0]) + 4 * (int)__ldg(row + xs[1]) + 6 * (int)__ldg(row + xs[2]) +
-               4 * (int)__ldg(row + xs[3]) + (int)__ldg(row + xs[4]);
     };
     int r0 = hrow(2 * oy0 - 2), r1 = hrow(2 * oy0 - 1), r2 = hrow(2 * oy0);
-#pragma unroll 2
+#pragma unroll 4
     for (int oy = oy0; oy < oy1; ++oy) {
         const int r3 = hrow(2 * oy + 1), r4 = hrow(2 * oy + 2);
         *((T*)((char*)dst + (size_t)oy * dp) + ox) = (T)((r0 + 4 * r1 + 6 * r2 + 4 * r3 + r4 + 128) >> 8);
@@ -81,6 +77,19 @@ __global__ void __launch_bounds__(kPdThreads) pyrdown_march_kernel(const T* __re
         r1 = r3;
         r2 = r4;
     }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kPdThreads) pyrdown_march_kernel(const T* __restrict__ src, size_t sp, int h, int w,
+                                                                   T* __restrict__ dst, size_t dp, int oh, int ow, int ybeg) {
+    const int ox = blockIdx.x * kPdThreads + threadIdx.x;
+    const int oy0 = ybeg + blockIdx.y * kPdRows;
+    if (ox >= ow || oy0 >= oh) return;
+    const int oy1 = min(oy0 + kPdRows, oh);
+    if (2 * ox >= 3 && 2 * ox + 3 < w)       // both pair alignments stay inside the row
+        pyrdown_march<T, true>(src, sp, h, w, dst, dp, ox, oy0, oy1);
+    else
+        pyrdown_march<T, false>(src, sp, h, w, dst, dp, ox, oy0, oy1);
 }
 
 __device__ __forceinline__ float2 mul2(float2 a, float s) { return make_float2(__fmul_rn(a.x, s), __fmul_rn(a.y, s)); }
