@@ -1,9 +1,8 @@
 #!/bin/bash
-timeout 110 python - <<'PY'
-import sys, runpy
-import pytest
-rc = pytest.main(["tests/test_gpu_ops.py", "tests/test_gpu_properties.py", "-m", "gpu", "-x", "-q", "-k", "pyr", "-p", "no:cacheprovider"])
-print("pytest rc", rc, flush=True)
-sys.argv = ["scripts/time_pyrdown.py"]
-runpy.run_path("scripts/time_pyrdown.py", run_name="__main__")
+timeout 100 python - <<'PY'
+import runpy, sys
+import __graft_entry__ as g
+g.smoke(); print("smoke ok", flush=True)
+sys.argv = ["scripts/e2e_pageable.py"]
+runpy.run_path("scripts/e2e_pageable.py", run_name="__main__")
 PY
